@@ -1,0 +1,156 @@
+/*
+ * scdd_b200.h -- C ABI of libscdd_b200.so: the B200 (sm_100a) implementation of scDD's
+ * per-gene mixture-fitting / permutation-testing / KS hot path.
+ *
+ * The reference (kdkorthauer/scDD 1.19.1) is pure R and has NO FFI today; this is the
+ * boundary its R shim binds through .Call (see INTEGRATION.md and r/src/scdd_glue.c).
+ * Each entry point names the reference interface it replaces (file:line relative to the
+ * reference tree).  Plain C: pointers + sizes, caller-allocated buffers, integer status
+ * (0 = ok, <0 = error; message via scdd_last_error()).  No torch / R types.
+ *
+ * There is NO CPU fallback: every compute entry point fails with SCDD_ERR_NO_DEVICE when
+ * no CUDA device is usable.
+ *
+ * Gene data layout ("CSR over genes"), shared by all entry points:
+ *   gene_off[ngenes+1]  int64   offsets into the per-gene value arrays
+ *   logy[nnz]           double  log of the NONZERO normalized counts of each gene, in cell order
+ *                               (R/scDD.R:374-375  `y <- log(y[y>0])`)
+ *   cond01[nnz]         int32   0 = reference condition (first level, R/scDD.R:258), 1 = other,
+ *                               for the same cells (`cond0 <- condition[y>0]`)
+ */
+#ifndef SCDD_B200_H
+#define SCDD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCDD_GMAX 5          /* Mclust(G = 1:5), R/mclust.restricted.R:52 */
+#define SCDD_ABI_VERSION 1
+
+enum {
+    SCDD_OK = 0,
+    SCDD_ERR_NO_DEVICE = -1,   /* no usable CUDA device (product path never falls back to CPU) */
+    SCDD_ERR_BAD_ARG = -2,
+    SCDD_ERR_CUDA = -3,
+    SCDD_ERR_TOO_LARGE = -4,   /* a fit-set has more points than the kernels support */
+    SCDD_ERR_FIT_FAILED = -5   /* some fit-set had no valid model (all BIC NA) -- outputs hold NaN there */
+};
+
+/* prior_param + the arguments of scDD() that reach the hot path (R/scDD.R:217-225, :245-249) */
+typedef struct {
+    double alpha, m0, s0, a0, b0;
+    int32_t min_size;      /* min.size */
+    int32_t restrict_;     /* mclustRestricted(restrict=) */
+    int32_t extra_mstep;   /* 1: mclust summaryMclustBIC's extra M-step on $parameters */
+    int32_t ks_old_pvalue; /* 1: R < 4.2 form `1 - pKS2` of the asymptotic KS p-value */
+} scdd_cfg;
+
+/* what mclustRestricted returns (R/mclust.restricted.R:249-252) minus `class` (separate array) */
+typedef struct {
+    int32_t G;        /* number of components == length(mean) */
+    int32_t model_v;  /* 0: modelName "X" (G = 1), 1: "V" */
+    int32_t n;
+    int32_t df;
+    double bic, loglik;
+    double mean[SCDD_GMAX], var[SCDD_GMAX];   /* ordered by increasing mean */
+} scdd_fit;
+
+/* work / diagnostics counters, accumulated over one call */
+typedef struct {
+    double triples;        /* sum over executed EM iterations of (points x components)  [SURVEY 8d: T] */
+    double point_iters;    /* sum over executed EM iterations of points                 [SURVEY 8d: P] */
+    double fit_sets;       /* mclustRestricted-equivalents evaluated */
+    double em_iters;       /* EM iterations summed over all G = 2..5 fits */
+    double iter_cap_hits;  /* EM fits stopped by the safety cap instead of the tolerance (expected 0) */
+    double tol_near;       /* EM fits whose stopping test was within 1e-7 (relative) of the tolerance */
+    double bic_near;       /* fit-sets whose two best BICs differ by < 1e-9 relative (near ties) */
+    double const_sets;     /* fit-sets with all values identical (reference would jitter with runif) */
+    double failed_sets;    /* fit-sets with no valid model */
+    double fit_kernel_ms;  /* device time of the mixture-fit kernel(s), CUDA events */
+    double fit_kernel_launches;
+    double rng_kernel_ms;  /* device time of the permutation-generation kernel(s) */
+    double total_ms;       /* device time of the whole call, first H2D to last D2H */
+    double h2d_bytes, d2h_bytes;
+} scdd_stats;
+
+/* ---- library / device management ---- */
+int32_t scdd_abi_version(void);
+const char* scdd_last_error(void);              /* thread-local message of the last failing call */
+int32_t scdd_device_count(void);                /* number of usable CUDA devices, 0 if none */
+int32_t scdd_set_devices(const int32_t* devices, int32_t n); /* devices later calls shard genes over (default: current device only) */
+void scdd_default_cfg(scdd_cfg* cfg);           /* scDD() defaults, R/scDD.R:217-225 */
+
+/* ---- observed-data fits:  genefit, R/scDD.R:327-340 and :373-391 ----
+ * fits[3*ngenes]: (oa, c1, c2) per gene.  cls_oa[nnz]: oa$class per nonzero cell.
+ * cls_c[nnz]: c1$class / c2$class scattered back to cell order.
+ * bf[ngenes] = jointPosterior(c1)+jointPosterior(c2), den[ngenes] = jointPosterior(oa)
+ * (R/scDD.R:381-383, R/joint.posterior.R:35-64); either may be NULL (permutations == 0 path). */
+int32_t scdd_fit_observed(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                          const scdd_cfg* cfg, scdd_fit* fits, int32_t* cls_oa, int32_t* cls_c,
+                          double* bf, double* den, scdd_stats* stats);
+
+/* ---- permutation Bayes-factor numerators:  permMclustGene R/permutations.R:211-286,
+ *      permMclust :147-181, permMclustCov :44-104 ----
+ * bf_perm[ngenes*B], gene-major.  Permutations come from exactly one of
+ *   perm_idx : the output of R's `sample(1:n_g)` (1-based), [sum_g n_g*B], gene-major then
+ *              permutation-major (host-drawn, R/permutations.R:273), or
+ *   seed6    : [ngenes*6] L'Ecuyer-CMRG states (.Random.seed[2:7]) -- one stream per gene as
+ *              BiocParallel gives each bplapply element (R/scDD.R:458); permutations are then
+ *              drawn ON THE DEVICE with a bit-exact re-implementation of R's sampler
+ *              (R_unif_index rejection sampling); seed6_out (nullable) receives the advanced states.
+ * cdr != NULL selects adjust.perms=TRUE (R/permutations.R:230-267): cdr[nnz] is the cellular
+ * detection rate C of each nonzero cell; residuals of lm(y ~ C) are permuted and oa is refitted,
+ * bf_perm = JP(c1)+JP(c2)-JP(oa). */
+int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                     int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                     const scdd_cfg* cfg, double* bf_perm, uint32_t* seed6_out, scdd_stats* stats);
+
+/* ---- KS test:  testKS / onegene, R/Test_KS.R:55-65  (stats::ks.test(x1, x2, exact=FALSE)) ----
+ * vals[nnz]: the values to compare per gene (raw counts; zeros already dropped unless inclZero),
+ * D[ngenes], p[ngenes] (unadjusted).  D reproduces R's long-double cumsum bit for bit. */
+int32_t scdd_ks(const double* vals, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                int32_t old_pvalue, double* D, double* p, scdd_stats* stats);
+
+/* ---- R's RNG on the host (what the R shim gets for free from R itself) ----
+ * scdd_rng_gene_seeds: the L'Ecuyer-CMRG state BiocParallel hands to element i of
+ * bplapply(seq_len(ngenes), ..., BPPARAM = param) for RNGseed = seed:
+ * set.seed(seed, kind = "L'Ecuyer-CMRG") then one nextRNGSubStream per element.  out6: [ngenes*6]. */
+int32_t scdd_rng_gene_seeds(uint32_t seed, int32_t ngenes, uint32_t* out6);
+/* sample(1:n) x B from one L'Ecuyer state (host; 1-based output [B*n]); state advanced in place */
+int32_t scdd_rng_sample_perms(uint32_t* state6, int32_t n, int32_t B, int32_t* out);
+/* Mersenne-Twister path: set.seed(seed); then `count` calls of sample(1:n); out [count*n] */
+int32_t scdd_rng_mt_sample_perms(uint32_t seed, int32_t n, int32_t count, int32_t* out);
+
+/* ---- device-resident plan (throughput harness; inputs stay in HBM between steps) ---- */
+typedef struct scdd_plan scdd_plan;
+/* uploads the gene block to `device`, runs the per-gene preparation kernels.
+ * chunk_perms: permutations processed per scdd_plan_run_chunk call. */
+scdd_plan* scdd_plan_create(int32_t device, const double* logy, const int64_t* gene_off, const int32_t* cond01,
+                            int32_t ngenes, const scdd_cfg* cfg, int32_t chunk_perms, const uint32_t* seed6,
+                            const double* cdr);
+/* enqueues permutation generation + mixture fits + BF combine for the next `nperms` (<= chunk_perms)
+ * permutations of every resident gene on `cuda_stream` (a cudaStream_t, 0 = default stream).
+ * Asynchronous.  Results land in the plan's device buffer bf_chunk[ngenes*chunk_perms]. */
+int32_t scdd_plan_run_chunk(scdd_plan* plan, void* cuda_stream, int32_t nperms);
+/* device pointer of bf_chunk (for a D2H copy by the caller) */
+void* scdd_plan_bf_device_ptr(scdd_plan* plan);
+/* synchronises the device and reads the counters accumulated since plan creation */
+int32_t scdd_plan_stats(scdd_plan* plan, scdd_stats* stats);
+void scdd_plan_destroy(scdd_plan* plan);
+
+/* ---- host-side self checks (no GPU needed) ---- */
+/* software x87 extended-precision accumulate used by the KS kernel, run on the host:
+ * out[i] = (double)(long-double running sum of steps[0..i]) */
+int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out);
+/* the kernels' exp() on the host build of the same source: out[i] = exp(x[i]) for x in [-708, 0] */
+int32_t scdd_selftest_exp(const double* x, int32_t n, double* out);
+/* measured fp64 FMA throughput of the device (TFLOP/s, DFMA = 2 flop), used as the roofline denominator */
+double scdd_measure_fp64_peak(int32_t device, double* sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDD_B200_H */

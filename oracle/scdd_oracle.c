@@ -91,6 +91,9 @@ static void qclass_new(const double* x, const double* xs, int n, int k, int* cl)
     double* q = (double*)malloc(sizeof(double) * cap);
     while (L < k + 1) {
         nq += 1;
+        /* R would keep growing the grid (forever when the data has too few distinct values); the
+           restatement and the CUDA kernels both stop at 64 grid points and keep the last grid */
+        if (nq > 64) break;
         if (nq > cap) { cap = nq * 2; q = (double*)realloc(q, sizeof(double) * cap); }
         /* seq(0, 1, length = nq): c(0, (1:(nq-2)) * (1/(nq-1)), 1) */
         double by = 1.0 / (double)(nq - 1);
@@ -102,7 +105,6 @@ static void qclass_new(const double* x, const double* xs, int n, int k, int* cl)
             for (int m = 0; m < L; m++) if (q[m] == v) { dup = 1; break; }   /* unique() */
             if (!dup) q[L++] = v;
         }
-        if (nq > 4 * n + 64) break; /* safety: cannot happen for non-constant data */
     }
     if (L > k + 1) {
         /* q <- q[-order(diff(q))[1:nr]] ; stable ascending order of the gaps */

@@ -1,0 +1,347 @@
+// kernels.cuh -- the __global__ kernels of libscdd_b200 (sm_100a).
+//
+//   prep_partition_kernel   per gene: positions of the reference-condition cells first (stable), n1
+//   prep_lm_kernel          per gene: lm(y ~ C) fitted values and residuals (adjust.perms path)
+//   permgen_kernel          per gene: B x sample(1:n) with R's L'Ecuyer-CMRG + rejection sampler
+//   fit_kernel              persistent warps, one fit-set per warp at a time (fitset.cuh)
+//   combine_kernel          bf.perm = JP(c1) + JP(c2) [- JP(oa)]
+//   ks_kernel               per gene: stable sort of c(x, y), x87-exact cumsum, D
+//   fp64_peak_kernel        DFMA throughput microbenchmark (roofline denominator)
+#pragma once
+#include <cstdint>
+
+#include "../../include/scdd_b200.h"
+#include "fitset.cuh"
+#include "rrng.h"
+
+namespace scdd {
+
+// ------------------------------------------------------------------------------------------------
+// gene preparation
+// ------------------------------------------------------------------------------------------------
+// part[off_g + j], j < n1_g: positions (within the gene's nonzero cells) of the cells with cond == 0,
+// in cell order; then the cond != 0 cells.  new.y[cond == ref] of the reference is a gather through it.
+__global__ void prep_partition_kernel(const int32_t* __restrict__ cond, const int64_t* __restrict__ off,
+                                      int ngenes, uint32_t* __restrict__ part, int32_t* __restrict__ n1) {
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= ngenes) return;
+    int64_t o = off[g];
+    int n = (int)(off[g + 1] - o);
+    int c0 = 0;
+    for (int i = lane; i < n; i += 32) c0 += (cond[o + i] == 0) ? 1 : 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c0 += __shfl_xor_sync(FULLMASK, c0, s);
+    if (lane == 0) n1[g] = c0;
+    int r0 = 0, r1 = c0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        bool v = i < n;
+        int c = v ? cond[o + i] : 0;
+        unsigned m0 = __ballot_sync(FULLMASK, v && c == 0);
+        unsigned m1 = __ballot_sync(FULLMASK, v && c != 0);
+        unsigned lt = (1u << lane) - 1u;
+        if (v) {
+            if (c == 0) part[o + r0 + __popc(m0 & lt)] = (uint32_t)i;
+            else part[o + r1 + __popc(m1 & lt)] = (uint32_t)i;
+        }
+        r0 += __popc(m0);
+        r1 += __popc(m1);
+    }
+}
+
+// lm(y ~ C) per gene (R/permutations.R:232-234): ordinary least squares with intercept.
+__global__ void prep_lm_kernel(const double* __restrict__ y, const double* __restrict__ C,
+                               const int64_t* __restrict__ off, int ngenes,
+                               double* __restrict__ fitted, double* __restrict__ resid) {
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= ngenes) return;
+    int64_t o = off[g];
+    int n = (int)(off[g + 1] - o);
+    double sx = 0.0, sy = 0.0;
+    for (int i = lane; i < n; i += 32) { sx += C[o + i]; sy += y[o + i]; }
+    sx = warp_sum(sx); sy = warp_sum(sy);
+    double mx = sx / n, my = sy / n;
+    double sxx = 0.0, sxy = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        double dx = C[o + i] - mx;
+        sxx = fma(dx, dx, sxx);
+        sxy = fma(dx, y[o + i] - my, sxy);
+    }
+    sxx = warp_sum(sxx); sxy = warp_sum(sxy);
+    double b1 = sxy / sxx, b0 = my - b1 * mx;
+    for (int i = lane; i < n; i += 32) {
+        double f = __dadd_rn(b0, __dmul_rn(b1, C[o + i]));
+        fitted[o + i] = f;
+        resid[o + i] = y[o + i] - f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// permutations: thread per gene, nb consecutive sample(1:n) draws from the gene's own stream
+// (BiocParallel gives every bplapply element its own L'Ecuyer-CMRG stream, R/scDD.R:458).
+// perm_out layout: gene g, permutation b (local), element i -> perm_out[off_g * nb + b * n_g + i], 0-based.
+// ------------------------------------------------------------------------------------------------
+template <class IdxT>
+__global__ void permgen_kernel(const int64_t* __restrict__ off, int ngenes, uint32_t* __restrict__ seeds,
+                               IdxT* __restrict__ scratch, IdxT* __restrict__ perm_out, int nb) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngenes) return;
+    int64_t o = off[g];
+    uint32_t n = (uint32_t)(off[g + 1] - o);
+    LecuyerGen gen;
+#pragma unroll
+    for (int j = 0; j < 6; j++) gen.st.s[j] = seeds[(size_t)g * 6 + j];
+    IdxT* sc = scratch + o;
+    IdxT* out = perm_out + (size_t)o * nb;
+    for (int b = 0; b < nb; b++) {
+        r_sample_perm(gen, n, sc, out);
+        out += n;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) seeds[(size_t)g * 6 + j] = gen.st.s[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixture fits
+// ------------------------------------------------------------------------------------------------
+enum PermKind { PERM_NONE = 0, PERM_I32_1BASED = 1, PERM_U16 = 2, PERM_U32 = 3 };
+
+struct FitArgs {
+    const double* vals;        // logy, or lm residuals on the adjusted path
+    const double* fitted;      // nullptr, or lm fitted values (adjusted path): x = log(exp(fitted + resid[perm]))
+    const int64_t* gene_off;
+    const uint32_t* part;
+    const int32_t* n1;
+    const void* perm;          // nullptr = identity (observed data)
+    long long perm_bstride;    // permutations per gene stored in `perm`
+    int perm_kind;
+    int perm_b0;               // first permutation of this launch inside `perm`
+    int ngenes, nb, sets;      // sets per (gene, permutation): 2 = (c1, c2), 3 = (c1, c2, oa)
+    int np_max;                // slab capacity (power of two)
+    double* jp;                // [ngenes * nb * sets] log joint posterior of each fit-set
+    scdd_fit* fits;            // observed-data detail outputs (nullable): [3 * ngenes] as (oa, c1, c2)
+    int32_t* cls_oa;
+    int32_t* cls_c;
+    DevCfg cfg;
+    unsigned long long* work_counter;
+    double* stats;             // [9] global accumulators (WarpStats order)
+};
+
+__device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int n, int b, uint32_t i) {
+    if (a.perm_kind == PERM_NONE) return i;
+    size_t at = (size_t)o * (size_t)a.perm_bstride + (size_t)(a.perm_b0 + b) * (size_t)n + i;
+    if (a.perm_kind == PERM_U16) return (uint32_t)((const uint16_t*)a.perm)[at];
+    if (a.perm_kind == PERM_U32) return ((const uint32_t*)a.perm)[at];
+    return (uint32_t)(((const int32_t*)a.perm)[at] - 1);
+}
+
+template <int G>
+__device__ __forceinline__ int label_of(const Row& r, double x) {
+    double mu[G], nh[G], lc[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) { mu[k] = r.mu_em[k]; nh[k] = r.nh_em[k]; lc[k] = r.lc_em[k]; }
+    return map_label<G>(x, mu, nh, lc);
+}
+
+constexpr int FIT_MAX_WARPS = 16;
+
+__global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)a.np_max * sizeof(double) + GMAX * sizeof(Row);
+    double* xs = reinterpret_cast<double*>(smem_raw + warp * per_warp);
+    Row* rows = reinterpret_cast<Row*>(xs + a.np_max);
+    WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long total = (long long)a.ngenes * a.nb * a.sets;
+    const double NaN = nan("");
+
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ULL);
+        item = __shfl_sync(FULLMASK, item, 0);
+        if (item >= total) break;
+        const int w = (int)(item % a.sets);
+        const long long u = item / a.sets;
+        const int b = (int)(u % a.nb);
+        const int g = (int)(u / a.nb);
+        const int64_t o = a.gene_off[g];
+        const int ng = (int)(a.gene_off[g + 1] - o);
+        const int n1 = a.n1[g];
+        int n, pofs;
+        if (w == 0) { n = n1; pofs = 0; }
+        else if (w == 1) { n = ng - n1; pofs = n1; }
+        else { n = ng; pofs = 0; }                       // oa on c(y1, y2)
+
+        // ---- gather the (permuted) subset into the slab, pad to a power of two, sort ----
+        int np = 2;
+        while (np < n) np <<= 1;
+        for (int j = lane; j < np; j += 32) {
+            double v = INFINITY;
+            if (j < n) {
+                uint32_t i = a.part[o + pofs + j];
+                uint32_t src = perm_lookup(a, o, ng, b, i);
+                v = a.vals[o + src];
+                if (a.fitted) v = log(exp(a.fitted[o + i] + v));   // R/permutations.R:244,251-252
+            }
+            xs[j] = v;
+        }
+        __syncwarp();
+        warp_sort(xs, np, lane);
+
+        double jp = NaN;
+        int comps = 0;
+        if (n < 1 || xs[0] == xs[n - 1]) {
+            // all values identical: the reference jitters with runif() (R/mclust.restricted.R:48-50),
+            // which consumes RNG state mid-stream; reported, never silently fitted
+            st.const_sets += 1.0;
+            st.failed_sets += 1.0;
+        } else {
+            comps = fit_set(xs, n, lane, rows, a.cfg, st);
+            if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
+        }
+        if (lane == 0) a.jp[item] = jp;
+
+        // ---- observed-data detail: the list mclustRestricted returns ----
+        if (a.fits) {
+            scdd_fit* f = &a.fits[3 * (size_t)g + (w == 2 ? 0 : w + 1)];
+            int32_t* cls = (w == 2) ? a.cls_oa : a.cls_c;
+            int ord[GMAX] = {0, 1, 2, 3, 4};
+            if (comps > 0) {
+                const Row& mc = rows[comps - 1];
+                if (comps > 1) mean_order(mc, comps, ord);
+                if (lane == 0) {
+                    f->G = comps; f->model_v = comps > 1; f->n = n; f->df = comps > 1 ? 3 * comps - 1 : 2;
+                    f->bic = mc.bic; f->loglik = mc.loglik;
+                    for (int k = 0; k < GMAX; k++) {
+                        f->mean[k] = k < comps ? mc.mean[ord[k]] : NaN;
+                        f->var[k] = k < comps ? mc.sigsq[ord[k]] : NaN;
+                    }
+                }
+                for (int j = lane; j < n; j += 32) {
+                    uint32_t i = a.part[o + pofs + j];
+                    double x = a.vals[o + perm_lookup(a, o, ng, b, i)];
+                    int l = 0;
+                    switch (comps) {
+                        case 2: l = label_of<2>(mc, x); break;
+                        case 3: l = label_of<3>(mc, x); break;
+                        case 4: l = label_of<4>(mc, x); break;
+                        case 5: l = label_of<5>(mc, x); break;
+                        default: l = 0;
+                    }
+                    cls[o + i] = (comps > 1 ? ord[l] : l) + 1;   // R/mclust.restricted.R:243-247
+                }
+            } else {
+                if (lane == 0) {
+                    f->G = 0; f->model_v = 0; f->n = n; f->df = 0; f->bic = NaN; f->loglik = NaN;
+                    for (int k = 0; k < GMAX; k++) { f->mean[k] = NaN; f->var[k] = NaN; }
+                }
+                for (int j = lane; j < n; j += 32) cls[o + a.part[o + pofs + j]] = 0;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- flush the work counters ----
+    double v[9] = {st.triples, st.point_iters, st.em_iters, st.cap_hits, st.tol_near,
+                   st.bic_near, st.const_sets, st.failed_sets, st.fit_sets};
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (v[k] != 0.0) atomicAdd(&a.stats[k], v[k]);
+    }
+}
+
+// bf.perm[g, b] = JP(c1) + JP(c2) [- JP(oa)]   (R/permutations.R:265-267, :281-282)
+__global__ void combine_kernel(const double* __restrict__ jp, int ngenes, int nb, int sets,
+                               double* __restrict__ bf, long long ld, int col0) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)ngenes * nb) return;
+    int b = (int)(t % nb);
+    long long g = t / nb;
+    const double* p = jp + t * sets;
+    double v = __dadd_rn(p[0], p[1]);
+    if (sets == 3) v = __dsub_rn(v, p[2]);
+    bf[g * ld + col0 + b] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KS: D of stats::ks.test(x, y, exact = FALSE) -- z <- cumsum(ifelse(order(c(x, y)) <= n.x, 1/n.x, -1/n.y)),
+// ties keep the last element of each run, D = max |z|.  order() is stable, cumsum() accumulates in
+// x87 extended precision (LDOUBLE) and stores doubles; both are reproduced exactly.
+// One CTA per gene: bitonic sort of (value, position-in-c(x,y)) pairs in shared memory, then a serial
+// extended-precision scan by thread 0 (the rounding sequence is inherently serial).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t orderable(double v) {
+    if (v == 0.0) v = 0.0;   // -0 -> +0
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+__global__ void ks_kernel(const double* __restrict__ vals, const int64_t* __restrict__ off,
+                          const uint32_t* __restrict__ part, const int32_t* __restrict__ n1, int ngenes,
+                          int np_max, double* __restrict__ D) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* idx = reinterpret_cast<uint32_t*>(key + np_max);
+    for (int g = blockIdx.x; g < ngenes; g += gridDim.x) {
+        int64_t o = off[g];
+        int n = (int)(off[g + 1] - o);
+        int nx = n1[g], ny = n - nx;
+        if (nx < 1 || ny < 1) {   // ks.test: "not enough 'x' data" / "not enough 'y' data"
+            if (threadIdx.x == 0) D[g] = nan("");
+            continue;
+        }
+        int np = 2;
+        while (np < n) np <<= 1;
+        for (int j = threadIdx.x; j < np; j += blockDim.x) {
+            key[j] = (j < n) ? orderable(vals[o + part[o + j]]) : ~0ULL;
+            idx[j] = (uint32_t)j;
+        }
+        __syncthreads();
+        for (int k = 2; k <= np; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    int l = i | j;
+                    bool up = ((i & k) == 0);
+                    uint64_t ka = key[i], kb = key[l];
+                    uint32_t ia = idx[i], ib = idx[l];
+                    bool gt = (ka > kb) || (ka == kb && ia > ib);
+                    if (gt == up) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            const double cx = 1.0 / (double)nx, cy = -1.0 / (double)ny;
+            const Ext80 ex = ext_from_double(cx), ey = ext_from_double(cy);
+            Ext80 run = ext_zero();
+            double dmax = 0.0;
+            for (int i = 0; i < n; i++) {
+                run = ext_add(run, idx[i] < (uint32_t)nx ? ex : ey);
+                if (i == n - 1 || key[i + 1] != key[i]) {
+                    double z = fabs(ext_to_double(run));
+                    if (z > dmax) dmax = z;
+                }
+            }
+            D[g] = dmax;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DFMA throughput: 8 independent chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, c = 1e-9 * (threadIdx.x + 1);
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace scdd

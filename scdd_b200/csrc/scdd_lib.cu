@@ -1,0 +1,882 @@
+// scdd_lib.cu -- host side of libscdd_b200.so: the C ABI of include/scdd_b200.h on top of the kernels.
+//
+// One Pipeline object per device holds a gene block resident in HBM and drives
+//   permgen (R sampler) -> fit (mixture fits + restricted selection + PPM score) -> combine
+// per chunk of permutations.  Multi-GPU calls shard genes over devices (one host thread per device,
+// no collective: every gene is independent -- SURVEY 8e).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace scdd;
+
+// ------------------------------------------------------------------------------------------------
+// errors / device list
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::vector<int> g_devices;   // empty = current device
+
+struct ScddError {
+    int code;
+    std::string msg;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw ScddError{SCDD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)};    \
+    } while (0)
+
+static int fail(int code, const std::string& m) {
+    g_err = m;
+    return code;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count) CK(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+};
+
+static int device_count_quiet() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// R's RNG on the host (set.seed for L'Ecuyer-CMRG and Mersenne-Twister, stream jumps)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+uint32_t lcg50(uint32_t seed) {   // RNG_Init: initial scrambling
+    for (int j = 0; j < 50; j++) seed = 69069u * seed + 1u;
+    return seed;
+}
+
+void set_seed_lecuyer(uint32_t seed, uint32_t* s6) {
+    seed = lcg50(seed);
+    for (int j = 0; j < 6; j++) { seed = 69069u * seed + 1u; s6[j] = seed; }
+    // FixupSeeds: components must be below the moduli (R re-randomises otherwise; practically unreachable)
+    for (int j = 0; j < 3; j++) if (s6[j] >= (uint32_t)MRG_M1) s6[j] = 0;
+    for (int j = 3; j < 6; j++) if (s6[j] >= (uint32_t)MRG_M2) s6[j] = 0;
+}
+
+typedef unsigned __int128 u128;
+struct Mat3 { uint64_t a[3][3]; };
+
+Mat3 matmul(const Mat3& x, const Mat3& y, uint64_t m) {
+    Mat3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            u128 s = 0;
+            for (int k = 0; k < 3; k++) s += (u128)x.a[i][k] * y.a[k][j];
+            r.a[i][j] = (uint64_t)(s % m);
+        }
+    return r;
+}
+
+// transition matrices of the two MRG components raised to 2^e (parallel::nextRNGStream: e = 127,
+// nextRNGSubStream: e = 76)
+void jump_matrices(int e, Mat3& A1, Mat3& A2) {
+    A1 = Mat3{{{0, 1, 0}, {0, 0, 1}, {(uint64_t)(MRG_M1 - 810728), 1403580, 0}}};
+    A2 = Mat3{{{0, 1, 0}, {0, 0, 1}, {(uint64_t)(MRG_M2 - 1370589), 0, 527612}}};
+    for (int i = 0; i < e; i++) { A1 = matmul(A1, A1, MRG_M1); A2 = matmul(A2, A2, MRG_M2); }
+}
+
+void apply_jump(const Mat3& A1, const Mat3& A2, const uint32_t* in, uint32_t* out) {
+    uint32_t t[6];
+    for (int i = 0; i < 3; i++) {
+        u128 s1 = 0, s2 = 0;
+        for (int k = 0; k < 3; k++) { s1 += (u128)A1.a[i][k] * in[k]; s2 += (u128)A2.a[i][k] * in[3 + k]; }
+        t[i] = (uint32_t)(s1 % (uint64_t)MRG_M1);
+        t[3 + i] = (uint32_t)(s2 % (uint64_t)MRG_M2);
+    }
+    std::memcpy(out, t, sizeof(t));
+}
+
+struct MersenneTwister {   // R's default kind
+    uint32_t mt[624];
+    int mti;
+    void seed(uint32_t s) {
+        s = lcg50(s);
+        s = 69069u * s + 1u;   // i_seed[0] (the mti slot), overwritten by FixupSeeds
+        for (int j = 0; j < 624; j++) { s = 69069u * s + 1u; mt[j] = s; }
+        mti = 624;
+    }
+    SCDD_RNG_HD double unif() {
+        uint32_t y;
+        if (mti >= 624) {
+            int kk;
+            for (kk = 0; kk < 624 - 397; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            for (; kk < 623; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            mti = 0;
+        }
+        y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return r_fixup((double)y * 2.3283064365386963e-10);
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Pipeline: one gene block resident on one device
+// ------------------------------------------------------------------------------------------------
+struct Pipeline {
+    int device = 0;
+    int ngenes = 0;
+    size_t nnz = 0;
+    int max_n = 0, max_half = 0;
+    int n_sm = 0;
+    DevCfg cfg;
+    DevBuf<double> d_logy, d_cdr, d_fitted, d_resid, d_jp, d_bf, d_stats;
+    DevBuf<int64_t> d_off;
+    DevBuf<int32_t> d_cond, d_n1;
+    DevBuf<uint32_t> d_part, d_seeds;
+    DevBuf<unsigned long long> d_counter;
+    DevBuf<unsigned char> d_perm, d_scratch;
+    std::vector<int64_t> h_off;
+    bool adjusted = false;
+    bool wide_idx = false;   // permutation indices need 32 bits
+    int chunk_perms = 0;
+    // per-launch CUDA-event pairs, recorded on the launching stream and read back in read_stats()
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> ev_free, ev_pending;
+    double fit_ms = 0, rng_ms = 0, fit_launches = 0;
+    bool time_kernels = true;
+
+    ~Pipeline() {
+        for (auto& t : ev_free) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        for (auto& t : ev_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    }
+
+    Timed tick_begin(int kind, cudaStream_t s) {
+        Timed t;
+        if (!ev_free.empty()) { t = ev_free.back(); ev_free.pop_back(); }
+        else { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
+        t.kind = kind;
+        CK(cudaEventRecord(t.a, s));
+        return t;
+    }
+    void tick_end(Timed t, cudaStream_t s) {
+        CK(cudaEventRecord(t.b, s));
+        ev_pending.push_back(t);
+    }
+
+    static DevCfg to_dev(const scdd_cfg* c) {
+        DevCfg d;
+        d.alpha = c->alpha; d.m0 = c->m0; d.s0 = c->s0; d.a0 = c->a0; d.b0 = c->b0;
+        d.min_size = c->min_size; d.restrict_ = c->restrict_; d.extra_mstep = c->extra_mstep; d.pad = 0;
+        return d;
+    }
+
+    void upload(int dev, const double* logy, const int64_t* gene_off, const int32_t* cond01, int ng,
+                const scdd_cfg* c, const double* cdr, cudaStream_t s) {
+        device = dev;
+        CK(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        n_sm = prop.multiProcessorCount;
+        ngenes = ng;
+        cfg = to_dev(c);
+        h_off.assign(gene_off, gene_off + ng + 1);
+        const int64_t base = h_off[0];
+        for (auto& v : h_off) v -= base;
+        nnz = (size_t)h_off[ng];
+        max_n = 0;
+        for (int g = 0; g < ng; g++) max_n = std::max<int>(max_n, (int)(h_off[g + 1] - h_off[g]));
+        d_logy.alloc(nnz); d_off.alloc(ng + 1); d_cond.alloc(nnz); d_part.alloc(nnz); d_n1.alloc(ng);
+        d_stats.alloc(16); d_counter.alloc(1);
+        CK(cudaMemcpyAsync(d_logy.p, logy + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_off.p, h_off.data(), (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_cond.p, cond01 + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_stats.p, 0, 16 * sizeof(double), s));
+        const int wpb = 8;
+        const int blocks = (ng + wpb - 1) / wpb;
+        if (ng > 0) prep_partition_kernel<<<blocks, wpb * 32, 0, s>>>(d_cond.p, d_off.p, ng, d_part.p, d_n1.p);
+        CK(cudaGetLastError());
+        adjusted = cdr != nullptr;
+        if (adjusted) {
+            d_cdr.alloc(nnz); d_fitted.alloc(nnz); d_resid.alloc(nnz);
+            CK(cudaMemcpyAsync(d_cdr.p, cdr + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+            if (ng > 0) prep_lm_kernel<<<blocks, wpb * 32, 0, s>>>(d_logy.p, d_cdr.p, d_off.p, ng, d_fitted.p, d_resid.p);
+            CK(cudaGetLastError());
+        }
+        std::vector<int32_t> h_n1(ng);
+        CK(cudaMemcpyAsync(h_n1.data(), d_n1.p, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        max_half = 0;
+        for (int g = 0; g < ng; g++) {
+            int n = (int)(h_off[g + 1] - h_off[g]);
+            max_half = std::max(max_half, std::max(h_n1[g], n - h_n1[g]));
+        }
+        wide_idx = max_n > 65535;
+    }
+
+    size_t idx_bytes() const { return wide_idx ? 4 : 2; }
+
+    // launches the persistent fit kernel over ngenes x nb x sets fit-sets
+    void launch_fit(cudaStream_t s, FitArgs a, int nmax_points) {
+        int np = 2;
+        while (np < nmax_points) np <<= 1;
+        const size_t per_warp = (size_t)np * sizeof(double) + GMAX * sizeof(Row);
+        const size_t smem_cap = 227 * 1024;
+        int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
+        if (warps < 1)
+            throw ScddError{SCDD_ERR_TOO_LARGE, "a fit-set of " + std::to_string(nmax_points) +
+                            " points does not fit the shared-memory slab of the warp-per-fit kernel"};
+        const long long total = (long long)a.ngenes * a.nb * a.sets;
+        if (total == 0) return;
+        const size_t smem = per_warp * warps;
+        CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long want = (total + warps - 1) / warps;
+        int grid = (int)std::min<long long>(n_sm, want);
+        a.np_max = np;
+        a.work_counter = d_counter.p;
+        a.stats = d_stats.p;
+        a.cfg = cfg;
+        CK(cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), s));
+        Timed t;
+        if (time_kernels) t = tick_begin(0, s);
+        fit_kernel<<<grid, warps * 32, smem, s>>>(a);
+        CK(cudaGetLastError());
+        if (time_kernels) tick_end(t, s);
+        fit_launches += 1;
+    }
+
+    void harvest_times() {   // call after the stream is synchronised
+        for (auto& t : ev_pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) (t.kind == 0 ? fit_ms : rng_ms) += ms;
+            else cudaGetLastError();
+            ev_free.push_back(t);
+        }
+        ev_pending.clear();
+    }
+
+    FitArgs base_args() const {
+        FitArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.vals = adjusted ? d_resid.p : d_logy.p;
+        a.fitted = adjusted ? d_fitted.p : nullptr;
+        a.gene_off = d_off.p;
+        a.part = d_part.p;
+        a.n1 = d_n1.p;
+        a.ngenes = ngenes;
+        return a;
+    }
+
+    // device buffers for `bc` permutations per gene drawn on the device
+    void alloc_perm_chunk(int bc, const uint32_t* seed6, cudaStream_t s) {
+        chunk_perms = bc;
+        d_perm.alloc(nnz * (size_t)bc * idx_bytes());
+        d_scratch.alloc(nnz * idx_bytes());
+        d_seeds.alloc((size_t)ngenes * 6);
+        CK(cudaMemcpyAsync(d_seeds.p, seed6, (size_t)ngenes * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        const int sets = adjusted ? 3 : 2;
+        d_jp.alloc((size_t)ngenes * bc * sets);
+    }
+
+    // permgen + fit + combine for nb permutations; bf_out[g * ld + col0 + b]
+    void run_chunk_device_perms(cudaStream_t s, int nb, double* bf_out, long long ld, int col0) {
+        if (ngenes == 0 || nb == 0) return;
+        const int tpb = 64;
+        Timed tr;
+        if (time_kernels) tr = tick_begin(1, s);
+        if (wide_idx)
+            permgen_kernel<uint32_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
+                (uint32_t*)d_scratch.p, (uint32_t*)d_perm.p, nb);
+        else
+            permgen_kernel<uint16_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
+                (uint16_t*)d_scratch.p, (uint16_t*)d_perm.p, nb);
+        CK(cudaGetLastError());
+        if (time_kernels) tick_end(tr, s);
+        FitArgs a = base_args();
+        a.perm = d_perm.p;
+        a.perm_bstride = nb;
+        a.perm_kind = wide_idx ? PERM_U32 : PERM_U16;
+        a.perm_b0 = 0;
+        a.nb = nb;
+        a.sets = adjusted ? 3 : 2;
+        a.jp = d_jp.p;
+        launch_fit(s, a, adjusted ? max_n : max_half);
+        const long long units = (long long)ngenes * nb;
+        combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(d_jp.p, ngenes, nb, a.sets, bf_out, ld, col0);
+        CK(cudaGetLastError());
+    }
+
+    void read_stats(scdd_stats* st, cudaStream_t s) {
+        double h[16];
+        CK(cudaMemcpyAsync(h, d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        harvest_times();
+        st->triples += h[0]; st->point_iters += h[1]; st->em_iters += h[2]; st->iter_cap_hits += h[3];
+        st->tol_near += h[4]; st->bic_near += h[5]; st->const_sets += h[6]; st->failed_sets += h[7];
+        st->fit_sets += h[8];
+        st->fit_kernel_ms += fit_ms; st->rng_kernel_ms += rng_ms; st->fit_kernel_launches += fit_launches;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// gene sharding over devices (LPT greedy on the number of nonzero cells; contiguous ranges are kept
+// simple here: genes are dealt to the least-loaded device in decreasing size, then each device's
+// genes are processed as gathered sub-blocks)
+// ------------------------------------------------------------------------------------------------
+struct Shard {
+    int device;
+    std::vector<int> genes;           // original gene indices
+    std::vector<int64_t> off;         // local CSR
+    std::vector<double> logy, cdr;
+    std::vector<int32_t> cond;
+};
+
+static std::vector<int> active_devices() {
+    if (!g_devices.empty()) return g_devices;
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+    return std::vector<int>{cur};
+}
+
+static int check_common(const void* a, const void* b, const void* c, int ngenes, const scdd_cfg* cfg) {
+    if (ngenes < 0 || (ngenes > 0 && (!a || !b || !c)) || !cfg) return fail(SCDD_ERR_BAD_ARG, "null pointer or negative gene count");
+    if (device_count_quiet() < 1) return fail(SCDD_ERR_NO_DEVICE, "no CUDA device available: libscdd_b200 has no CPU fallback");
+    return SCDD_OK;
+}
+
+template <class F>
+static int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const ScddError& e) {
+        cudaGetLastError();
+        return fail(e.code, e.msg);
+    } catch (const std::exception& e) {
+        return fail(SCDD_ERR_CUDA, e.what());
+    }
+}
+
+// splits genes over devices; single-device calls alias the caller's arrays (no copy)
+static void make_shards(const std::vector<int>& devs, const int64_t* gene_off, int ngenes,
+                        std::vector<std::vector<int>>& assign) {
+    assign.assign(devs.size(), {});
+    if (devs.size() == 1) {
+        assign[0].resize(ngenes);
+        std::iota(assign[0].begin(), assign[0].end(), 0);
+        return;
+    }
+    std::vector<int> order(ngenes);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return (gene_off[x + 1] - gene_off[x]) > (gene_off[y + 1] - gene_off[y]);
+    });
+    std::vector<double> load(devs.size(), 0.0);
+    for (int g : order) {
+        size_t best = 0;
+        for (size_t d = 1; d < devs.size(); d++) if (load[d] < load[best]) best = d;
+        assign[best].push_back(g);
+        load[best] += (double)(gene_off[g + 1] - gene_off[g]);
+    }
+    for (auto& v : assign) std::sort(v.begin(), v.end());
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int32_t scdd_abi_version(void) { return SCDD_ABI_VERSION; }
+const char* scdd_last_error(void) { return g_err.c_str(); }
+int32_t scdd_device_count(void) { return device_count_quiet(); }
+
+int32_t scdd_set_devices(const int32_t* devices, int32_t n) {
+    if (n < 0 || (n > 0 && !devices)) return fail(SCDD_ERR_BAD_ARG, "bad device list");
+    int cnt = device_count_quiet();
+    std::vector<int> v;
+    for (int i = 0; i < n; i++) {
+        if (devices[i] < 0 || devices[i] >= cnt) return fail(SCDD_ERR_NO_DEVICE, "device index out of range");
+        v.push_back(devices[i]);
+    }
+    g_devices = v;
+    return SCDD_OK;
+}
+
+void scdd_default_cfg(scdd_cfg* c) {
+    c->alpha = 0.10; c->m0 = 0.0; c->s0 = 0.01; c->a0 = 0.01; c->b0 = 0.01;   // R/scDD.R:218
+    c->min_size = 3; c->restrict_ = 1; c->extra_mstep = 1; c->ks_old_pvalue = 0;
+}
+
+// ---------------------------------------------------------------- observed fits
+static void fit_observed_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng,
+                             const scdd_cfg* cfg, scdd_fit* fits, int32_t* cls_oa, int32_t* cls_c,
+                             double* bf, double* den, scdd_stats* st) {
+    if (ng == 0) return;
+    Pipeline P;
+    cudaStream_t s;
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreate(&s));
+    try {
+        P.upload(dev, logy, off, cond, ng, cfg, nullptr, s);
+        DevBuf<scdd_fit> d_fits;
+        DevBuf<int32_t> d_oa, d_c;
+        d_fits.alloc(3 * (size_t)ng); d_oa.alloc(P.nnz); d_c.alloc(P.nnz);
+        P.d_jp.alloc(3 * (size_t)ng);
+        FitArgs a = P.base_args();
+        a.nb = 1; a.sets = 3; a.jp = P.d_jp.p;
+        a.fits = d_fits.p; a.cls_oa = d_oa.p; a.cls_c = d_c.p;
+        P.launch_fit(s, a, P.max_n);
+        std::vector<double> jp(3 * (size_t)ng);
+        const int64_t base = off[0];
+        CK(cudaMemcpyAsync(fits, d_fits.p, 3 * (size_t)ng * sizeof(scdd_fit), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cls_oa + base, d_oa.p, P.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cls_c + base, d_c.p, P.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(jp.data(), P.d_jp.p, jp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        P.read_stats(st, s);
+        for (int g = 0; g < ng; g++) {
+            if (bf) bf[g] = jp[3 * (size_t)g] + jp[3 * (size_t)g + 1];   // R/scDD.R:381-382
+            if (den) den[g] = jp[3 * (size_t)g + 2];                     // :383
+        }
+        st->h2d_bytes += (double)P.nnz * 12 + (ng + 1) * 8.0;
+        st->d2h_bytes += 3.0 * ng * sizeof(scdd_fit) + P.nnz * 8.0 + jp.size() * 8.0;
+    } catch (...) {
+        cudaStreamDestroy(s);
+        throw;
+    }
+    CK(cudaStreamDestroy(s));
+}
+
+int32_t scdd_fit_observed(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                          const scdd_cfg* cfg, scdd_fit* fits, int32_t* cls_oa, int32_t* cls_c,
+                          double* bf, double* den, scdd_stats* stats) {
+    int rc = check_common(logy, gene_off, cond01, ngenes, cfg);
+    if (rc) return rc;
+    if (ngenes > 0 && (!fits || !cls_oa || !cls_c)) return fail(SCDD_ERR_BAD_ARG, "null output");
+    scdd_stats st;
+    std::memset(&st, 0, sizeof(st));
+    return guarded([&]() -> int {
+        // observed fits are 3 fit-sets per gene: one device is plenty; the first active device takes them
+        std::vector<int> devs = active_devices();
+        fit_observed_one(devs[0], logy, gene_off, cond01, ngenes, cfg, fits, cls_oa, cls_c, bf, den, &st);
+        if (stats) *stats = st;
+        if (st.failed_sets > 0) return fail(SCDD_ERR_FIT_FAILED, "some fit-sets had no valid model (constant values?)");
+        return SCDD_OK;
+    });
+}
+
+// ---------------------------------------------------------------- permutations
+struct PermJob {
+    int dev;
+    std::vector<int> genes;
+};
+
+static void perm_bf_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng, int B,
+                        const int32_t* perm_idx, const uint32_t* seed6, const double* cdr, const scdd_cfg* cfg,
+                        double* bf_perm, uint32_t* seed6_out, scdd_stats* st) {
+    if (ng == 0 || B == 0) return;
+    Pipeline P;
+    cudaStream_t s;
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreate(&s));
+    try {
+        cudaEvent_t t0, t1;
+        CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        CK(cudaEventRecord(t0, s));
+        P.upload(dev, logy, off, cond, ng, cfg, cdr, s);
+        P.d_bf.alloc((size_t)ng * B);
+        const int sets = P.adjusted ? 3 : 2;
+        const int64_t base = off[0];
+        double h2d = (double)P.nnz * 12 + (ng + 1) * 8.0 + (cdr ? P.nnz * 8.0 : 0.0);
+        if (perm_idx) {
+            // host-drawn permutations (the R shim's own sample() calls): whole table resident
+            const size_t cnt = P.nnz * (size_t)B;
+            DevBuf<int32_t> d_pi;
+            d_pi.alloc(cnt);
+            CK(cudaMemcpyAsync(d_pi.p, perm_idx + (size_t)base * B, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            h2d += cnt * 4.0;
+            // jp chunked over permutations to bound memory
+            int bc = (int)std::max<long long>(1, std::min<long long>(B, (1LL << 27) / std::max(1, ng * sets)));
+            P.d_jp.alloc((size_t)ng * bc * sets);
+            for (int b0 = 0; b0 < B; b0 += bc) {
+                int nb = std::min(bc, B - b0);
+                FitArgs a = P.base_args();
+                a.perm = d_pi.p; a.perm_bstride = B; a.perm_kind = PERM_I32_1BASED; a.perm_b0 = b0;
+                a.nb = nb; a.sets = sets; a.jp = P.d_jp.p;
+                P.launch_fit(s, a, P.adjusted ? P.max_n : P.max_half);
+                const long long units = (long long)ng * nb;
+                combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(P.d_jp.p, ng, nb, sets, P.d_bf.p, B, b0);
+                CK(cudaGetLastError());
+            }
+            CK(cudaStreamSynchronize(s));
+        } else {
+            // device-drawn permutations, chunked so the index buffer stays below ~2 GiB
+            long long per_perm = (long long)P.nnz * (long long)P.idx_bytes();
+            int bc = (int)std::max<long long>(1, std::min<long long>(B, (2LL << 30) / std::max<long long>(1, per_perm)));
+            bc = (int)std::min<long long>(bc, std::max<long long>(1, (1LL << 27) / std::max(1, ng * sets)));
+            P.alloc_perm_chunk(bc, seed6, s);
+            h2d += ng * 24.0;
+            for (int b0 = 0; b0 < B; b0 += bc) {
+                int nb = std::min(bc, B - b0);
+                P.run_chunk_device_perms(s, nb, P.d_bf.p, B, b0);
+            }
+            if (seed6_out)
+                CK(cudaMemcpyAsync(seed6_out, P.d_seeds.p, (size_t)ng * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaMemcpyAsync(bf_perm, P.d_bf.p, (size_t)ng * B * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(t1, s));
+        P.read_stats(st, s);
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        st->total_ms = std::max<double>(st->total_ms, ms);
+        st->h2d_bytes += h2d;
+        st->d2h_bytes += (double)ng * B * 8.0;
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    } catch (...) {
+        cudaStreamDestroy(s);
+        throw;
+    }
+    CK(cudaStreamDestroy(s));
+}
+
+int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                     int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                     const scdd_cfg* cfg, double* bf_perm, uint32_t* seed6_out, scdd_stats* stats) {
+    int rc = check_common(logy, gene_off, cond01, ngenes, cfg);
+    if (rc) return rc;
+    if (B < 0 || (ngenes > 0 && B > 0 && !bf_perm)) return fail(SCDD_ERR_BAD_ARG, "bad B / null output");
+    if ((perm_idx != nullptr) == (seed6 != nullptr) && ngenes > 0 && B > 0)
+        return fail(SCDD_ERR_BAD_ARG, "give exactly one of perm_idx (host-drawn) or seed6 (device-drawn)");
+    scdd_stats st;
+    std::memset(&st, 0, sizeof(st));
+    return guarded([&]() -> int {
+        std::vector<int> devs = active_devices();
+        std::vector<std::vector<int>> assign;
+        make_shards(devs, gene_off, ngenes, assign);
+        if (devs.size() == 1) {
+            perm_bf_one(devs[0], logy, gene_off, cond01, ngenes, B, perm_idx, seed6, cdr, cfg, bf_perm, seed6_out, &st);
+        } else {
+            // gather each device's genes into a private CSR block, run the shards concurrently, scatter back
+            std::vector<scdd_stats> sts(devs.size());
+            std::vector<ScddError> errs(devs.size(), ScddError{0, ""});
+            std::vector<std::thread> th;
+            for (size_t d = 0; d < devs.size(); d++) {
+                th.emplace_back([&, d]() {
+                    std::memset(&sts[d], 0, sizeof(scdd_stats));
+                    try {
+                        const std::vector<int>& gs = assign[d];
+                        const int ngl = (int)gs.size();
+                        if (ngl == 0) return;
+                        std::vector<int64_t> off(ngl + 1, 0);
+                        for (int i = 0; i < ngl; i++) off[i + 1] = off[i] + (gene_off[gs[i] + 1] - gene_off[gs[i]]);
+                        const size_t nz = (size_t)off[ngl];
+                        std::vector<double> ly(nz), cd;
+                        std::vector<int32_t> cc(nz), pi;
+                        std::vector<uint32_t> sd, sdo;
+                        if (cdr) cd.resize(nz);
+                        if (perm_idx) pi.resize(nz * (size_t)B);
+                        if (seed6) { sd.resize((size_t)ngl * 6); sdo.resize((size_t)ngl * 6); }
+                        for (int i = 0; i < ngl; i++) {
+                            const int g = gs[i];
+                            const size_t o = (size_t)gene_off[g], n = (size_t)(gene_off[g + 1] - gene_off[g]);
+                            std::memcpy(&ly[off[i]], logy + o, n * 8);
+                            std::memcpy(&cc[off[i]], cond01 + o, n * 4);
+                            if (cdr) std::memcpy(&cd[off[i]], cdr + o, n * 8);
+                            if (perm_idx) std::memcpy(&pi[(size_t)off[i] * B], perm_idx + o * (size_t)B, n * (size_t)B * 4);
+                            if (seed6) std::memcpy(&sd[(size_t)i * 6], seed6 + (size_t)g * 6, 24);
+                        }
+                        std::vector<double> out((size_t)ngl * B);
+                        perm_bf_one(devs[d], ly.data(), off.data(), cc.data(), ngl, B, perm_idx ? pi.data() : nullptr,
+                                    seed6 ? sd.data() : nullptr, cdr ? cd.data() : nullptr, cfg, out.data(),
+                                    seed6_out ? sdo.data() : nullptr, &sts[d]);
+                        for (int i = 0; i < ngl; i++) {
+                            std::memcpy(bf_perm + (size_t)gs[i] * B, &out[(size_t)i * B], (size_t)B * 8);
+                            if (seed6_out) std::memcpy(seed6_out + (size_t)gs[i] * 6, &sdo[(size_t)i * 6], 24);
+                        }
+                    } catch (const ScddError& e) {
+                        errs[d] = e;
+                    } catch (const std::exception& e) {
+                        errs[d] = ScddError{SCDD_ERR_CUDA, e.what()};
+                    }
+                });
+            }
+            for (auto& t : th) t.join();
+            for (auto& e : errs) if (e.code) throw e;
+            for (auto& s1 : sts) {
+                const double* src = reinterpret_cast<const double*>(&s1);
+                double* dst = reinterpret_cast<double*>(&st);
+                for (size_t k = 0; k < sizeof(scdd_stats) / sizeof(double); k++) dst[k] += src[k];
+                st.total_ms = std::max(st.total_ms, s1.total_ms);
+            }
+        }
+        if (stats) *stats = st;
+        if (st.failed_sets > 0) return fail(SCDD_ERR_FIT_FAILED, "some permuted fit-sets had no valid model; their bf_perm is NaN");
+        return SCDD_OK;
+    });
+}
+
+// ---------------------------------------------------------------- KS
+// asymptotic two-sided p-value of ks.test (R >= 4.2: psmirnov/pkolmogorov_two_limit upper tail;
+// older R: 1 - pKS2) -- evaluated on the host, one scalar series per gene
+static double ks_pvalue(double stat, int old_form) {
+    const double tol = 1e-6;
+    const int k_max = (int)std::sqrt(2.0 - std::log(tol));
+    const double PI = 3.14159265358979323846;
+    const double inv_sqrt_2pi = 0.398942280401432677939946059934;
+    double p;
+    if (stat <= 0) p = old_form ? 1.0 - 0.0 : 1.0;
+    else if (stat < 1.0) {
+        double z = -(PI / 2.0 * PI / 4.0) / (stat * stat), w = std::log(stat), s = 0.0;
+        for (int k = 1; k < k_max; k += 2) s += std::exp(k * k * z - w);
+        p = 1.0 - s / inv_sqrt_2pi;
+    } else if (!old_form) {
+        double z = -2.0 * stat * stat, sg = -1.0, old = 0.0, nw = 2.0 * std::exp(z);
+        int k = 2;
+        while (std::fabs(old - nw) > tol) { old = nw; nw += 2.0 * sg * std::exp(z * k * k); sg *= -1.0; k++; }
+        p = nw;
+    } else {
+        double z = -2.0 * stat * stat, sg = -1.0, old = 0.0, nw = 1.0;
+        int k = 1;
+        while (std::fabs(old - nw) > tol) { old = nw; nw += 2.0 * sg * std::exp(z * k * k); sg *= -1.0; k++; }
+        p = 1.0 - nw;
+    }
+    return std::min(1.0, std::max(0.0, p));
+}
+
+int32_t scdd_ks(const double* vals, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                int32_t old_pvalue, double* D, double* p, scdd_stats* stats) {
+    scdd_cfg cfg;
+    scdd_default_cfg(&cfg);
+    int rc = check_common(vals, gene_off, cond01, ngenes, &cfg);
+    if (rc) return rc;
+    if (ngenes > 0 && (!D || !p)) return fail(SCDD_ERR_BAD_ARG, "null output");
+    if (ngenes == 0) return SCDD_OK;
+    return guarded([&]() -> int {
+        std::vector<int> devs = active_devices();
+        Pipeline P;
+        cudaStream_t s;
+        CK(cudaSetDevice(devs[0]));
+        CK(cudaStreamCreate(&s));
+        std::vector<int32_t> h_n1(ngenes);
+        try {
+            P.upload(devs[0], vals, gene_off, cond01, ngenes, &cfg, nullptr, s);
+            int np = 2;
+            while (np < P.max_n) np <<= 1;
+            size_t smem = (size_t)np * 12;
+            if (smem > 227 * 1024)
+                throw ScddError{SCDD_ERR_TOO_LARGE, "KS: a gene with " + std::to_string(P.max_n) + " cells exceeds the shared-memory sort"};
+            DevBuf<double> d_D;
+            d_D.alloc(ngenes);
+            CK(cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / std::max<size_t>(smem, 1)));
+            int grid = std::min(ngenes, P.n_sm * per_sm);
+            cudaEvent_t t0, t1;
+            CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+            CK(cudaEventRecord(t0, s));
+            ks_kernel<<<grid, 128, smem, s>>>(P.d_logy.p, P.d_off.p, P.d_part.p, P.d_n1.p, ngenes, np, d_D.p);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(t1, s));
+            CK(cudaMemcpyAsync(D, d_D.p, ngenes * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_n1.data(), P.d_n1.p, ngenes * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (stats) {
+                std::memset(stats, 0, sizeof(*stats));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, t0, t1));
+                stats->total_ms = ms;
+                stats->h2d_bytes = (double)P.nnz * 12 + (ngenes + 1) * 8.0;
+                stats->d2h_bytes = ngenes * 12.0;
+            }
+            cudaEventDestroy(t0); cudaEventDestroy(t1);
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        CK(cudaStreamDestroy(s));
+        for (int g = 0; g < ngenes; g++) {
+            double nx = h_n1[g], ny = (double)(gene_off[g + 1] - gene_off[g]) - nx;
+            if (nx < 1 || ny < 1) { p[g] = NAN; continue; }
+            double en = nx * ny / (nx + ny);
+            p[g] = ks_pvalue(std::sqrt(en) * D[g], old_pvalue);
+        }
+        return SCDD_OK;
+    });
+}
+
+// ---------------------------------------------------------------- host RNG helpers
+int32_t scdd_rng_gene_seeds(uint32_t seed, int32_t ngenes, uint32_t* out6) {
+    if (ngenes < 0 || (ngenes > 0 && !out6)) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    uint32_t s[6];
+    set_seed_lecuyer(seed, s);
+    Mat3 A1, A2;
+    jump_matrices(76, A1, A2);   // nextRNGSubStream
+    for (int g = 0; g < ngenes; g++) {
+        std::memcpy(out6 + (size_t)g * 6, s, sizeof(s));
+        apply_jump(A1, A2, s, s);
+    }
+    return SCDD_OK;
+}
+
+int32_t scdd_rng_sample_perms(uint32_t* state6, int32_t n, int32_t B, int32_t* out) {
+    if (!state6 || n < 0 || B < 0 || (!out && (size_t)n * B > 0)) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    LecuyerGen gen;
+    std::memcpy(gen.st.s, state6, 24);
+    std::vector<int32_t> scratch(std::max(1, n));
+    for (int b = 0; b < B; b++) {
+        int32_t* o = out + (size_t)b * n;
+        r_sample_perm(gen, (uint32_t)n, scratch.data(), o);
+        for (int i = 0; i < n; i++) o[i] += 1;
+    }
+    std::memcpy(state6, gen.st.s, 24);
+    return SCDD_OK;
+}
+
+int32_t scdd_rng_mt_sample_perms(uint32_t seed, int32_t n, int32_t count, int32_t* out) {
+    if (n < 0 || count < 0 || (!out && (size_t)n * count > 0)) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    MersenneTwister mt;
+    mt.seed(seed);
+    std::vector<int32_t> scratch(std::max(1, n));
+    for (int b = 0; b < count; b++) {
+        int32_t* o = out + (size_t)b * n;
+        r_sample_perm(mt, (uint32_t)n, scratch.data(), o);
+        for (int i = 0; i < n; i++) o[i] += 1;
+    }
+    return SCDD_OK;
+}
+
+// ---------------------------------------------------------------- resident plan
+struct scdd_plan {
+    Pipeline P;
+    cudaStream_t own = nullptr;
+};
+
+scdd_plan* scdd_plan_create(int32_t device, const double* logy, const int64_t* gene_off, const int32_t* cond01,
+                            int32_t ngenes, const scdd_cfg* cfg, int32_t chunk_perms, const uint32_t* seed6,
+                            const double* cdr) {
+    if (check_common(logy, gene_off, cond01, ngenes, cfg)) return nullptr;
+    if (!seed6 || chunk_perms < 1 || ngenes < 1) { fail(SCDD_ERR_BAD_ARG, "plan needs seed6, chunk_perms >= 1, ngenes >= 1"); return nullptr; }
+    scdd_plan* pl = nullptr;
+    int rc = guarded([&]() -> int {
+        pl = new scdd_plan();
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreate(&pl->own));
+        pl->P.upload(device, logy, gene_off, cond01, ngenes, cfg, cdr, pl->own);
+        pl->P.alloc_perm_chunk(chunk_perms, seed6, pl->own);
+        pl->P.d_bf.alloc((size_t)ngenes * chunk_perms);
+        CK(cudaStreamSynchronize(pl->own));
+        return SCDD_OK;
+    });
+    if (rc) { delete pl; return nullptr; }
+    return pl;
+}
+
+int32_t scdd_plan_run_chunk(scdd_plan* plan, void* cuda_stream, int32_t nperms) {
+    if (!plan || nperms < 1 || nperms > plan->P.chunk_perms) return fail(SCDD_ERR_BAD_ARG, "bad plan / nperms");
+    return guarded([&]() -> int {
+        CK(cudaSetDevice(plan->P.device));
+        plan->P.run_chunk_device_perms((cudaStream_t)cuda_stream, nperms, plan->P.d_bf.p, plan->P.chunk_perms, 0);
+        return SCDD_OK;
+    });
+}
+
+void* scdd_plan_bf_device_ptr(scdd_plan* plan) { return plan ? plan->P.d_bf.p : nullptr; }
+
+int32_t scdd_plan_stats(scdd_plan* plan, scdd_stats* stats) {
+    if (!plan || !stats) return fail(SCDD_ERR_BAD_ARG, "null");
+    return guarded([&]() -> int {
+        CK(cudaSetDevice(plan->P.device));
+        CK(cudaDeviceSynchronize());
+        std::memset(stats, 0, sizeof(*stats));
+        plan->P.read_stats(stats, plan->own);
+        return SCDD_OK;
+    });
+}
+
+void scdd_plan_destroy(scdd_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->P.device);
+    cudaDeviceSynchronize();
+    if (plan->own) cudaStreamDestroy(plan->own);
+    delete plan;
+}
+
+// ---------------------------------------------------------------- self tests / peak
+int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out) {
+    Ext80 run = ext_zero();
+    for (int i = 0; i < n; i++) {
+        run = ext_add(run, ext_from_double(steps[i]));
+        out[i] = ext_to_double(run);
+    }
+    return SCDD_OK;
+}
+
+int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
+    for (int i = 0; i < n; i++) out[i] = exp_neg(x[i]);
+    return SCDD_OK;
+}
+
+double scdd_measure_fp64_peak(int32_t device, double* sm_clock_mhz_out) {
+    if (device_count_quiet() < 1) { fail(SCDD_ERR_NO_DEVICE, "no CUDA device"); return -1.0; }
+    double result = -1.0;
+    guarded([&]() -> int {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 14;
+        DevBuf<double> out;
+        out.alloc((size_t)blocks * threads);
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; rep++) {
+            CK(cudaEventRecord(a));
+            fp64_peak_kernel<<<blocks, threads>>>(out.p, iters, 1.0 + rep);
+            CK(cudaEventRecord(b));
+            CK(cudaEventSynchronize(b));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        if (sm_clock_mhz_out) {
+            int khz = 0;
+            cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+            *sm_clock_mhz_out = khz / 1000.0;
+        }
+        result = best;
+        return SCDD_OK;
+    });
+    return result;
+}
+
+}  // extern "C"

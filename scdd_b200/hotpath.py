@@ -1,0 +1,171 @@
+"""numpy-level wrappers of the C ABI (include/scdd_b200.h): marshalling only, no arithmetic of the hot path.
+
+Function names mirror the reference's internal interface for this path:
+  fit_observed  <-> genefit (R/scDD.R:327-340, :373-391): mclustRestricted x3 + jointPosterior
+  perm_bf       <-> permMclustGene / permMclust / permMclustCov (R/permutations.R)
+  ks            <-> testKS::onegene (R/Test_KS.R:56-65)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FIT_DTYPE, Stats, make_cfg, ScddError  # noqa: F401
+
+
+def gene_csr(normcounts, condition, ref=None, log=True, incl_zero=False):
+    """Dense genes x cells matrix -> the CSR-over-genes layout of the C ABI.
+
+    Returns (vals, cond01, gene_off): per gene the (log) nonzero values in cell order
+    (`y <- log(y[y>0])`, R/scDD.R:374-375) and 0/1 condition labels (0 = reference = first level,
+    R/scDD.R:258).  incl_zero keeps zeros (testKS(inclZero=TRUE), values not logged)."""
+    X = np.asarray(normcounts, dtype=np.float64)
+    condition = np.asarray(condition)
+    if ref is None:
+        ref = condition[0]
+    c01 = (condition != ref).astype(np.int32)
+    mask = np.ones_like(X, dtype=bool) if incl_zero else (X > 0)
+    counts = mask.sum(axis=1)
+    gene_off = np.zeros(X.shape[0] + 1, dtype=np.int64)
+    np.cumsum(counts, out=gene_off[1:])
+    vals = X[mask]                      # row-major boolean indexing keeps cell order within each gene
+    if log:
+        vals = np.log(vals)
+    cond01 = np.broadcast_to(c01, X.shape)[mask].astype(np.int32)
+    return np.ascontiguousarray(vals), np.ascontiguousarray(cond01), gene_off
+
+
+def _prep(vals, cond01, gene_off):
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    cond01 = np.ascontiguousarray(cond01, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    assert gene_off.ndim == 1 and gene_off.size >= 1
+    assert vals.size >= gene_off[-1] and cond01.size >= gene_off[-1]
+    return vals, cond01, gene_off
+
+
+def set_devices(devices):
+    d = np.ascontiguousarray(devices, dtype=np.int32)
+    _lib.check(_lib.lib().scdd_set_devices(d.ctypes.data_as(C.POINTER(C.c_int32)), d.size))
+
+
+def device_count():
+    return _lib.lib().scdd_device_count()
+
+
+def fit_observed(logy, cond01, gene_off, cfg=None, with_bf=True, allow_failed=False):
+    """Returns (fits[ngenes, 3] structured (oa, c1, c2), cls_oa[nnz], cls_c[nnz], bf, den, stats)."""
+    cfg = cfg or make_cfg()
+    logy, cond01, gene_off = _prep(logy, cond01, gene_off)
+    ng = gene_off.size - 1
+    fits = np.zeros((ng, 3), dtype=FIT_DTYPE)
+    cls_oa = np.zeros(logy.size, dtype=np.int32)
+    cls_c = np.zeros(logy.size, dtype=np.int32)
+    bf = np.zeros(ng) if with_bf else None
+    den = np.zeros(ng) if with_bf else None
+    st = Stats()
+    rc = _lib.lib().scdd_fit_observed(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, C.byref(cfg),
+                                      fits.ctypes.data, cls_oa.ctypes.data, cls_c.ctypes.data,
+                                      _lib.ptr(bf), _lib.ptr(den), C.byref(st))
+    _lib.check(rc, allow=(_lib.ERR_FIT_FAILED,) if allow_failed else ())
+    return fits, cls_oa, cls_c, bf, den, st.as_dict()
+
+
+def perm_bf(logy, cond01, gene_off, B, perm_idx=None, seed6=None, cdr=None, cfg=None, allow_failed=False,
+            return_seeds=False):
+    """Bayes-factor numerators of B permutations per gene: array [ngenes, B] (+ stats dict)."""
+    cfg = cfg or make_cfg()
+    logy, cond01, gene_off = _prep(logy, cond01, gene_off)
+    ng = gene_off.size - 1
+    out = np.zeros((ng, B))
+    if perm_idx is not None:
+        perm_idx = np.ascontiguousarray(perm_idx, dtype=np.int32)
+        assert perm_idx.size == gene_off[-1] * B
+    if seed6 is not None:
+        seed6 = np.ascontiguousarray(seed6, dtype=np.uint32).reshape(ng, 6)
+    if cdr is not None:
+        cdr = np.ascontiguousarray(cdr, dtype=np.float64)
+        assert cdr.size == logy.size
+    seeds_out = np.zeros((ng, 6), dtype=np.uint32) if (return_seeds and seed6 is not None) else None
+    st = Stats()
+    rc = _lib.lib().scdd_perm_bf(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, int(B),
+                                 _lib.ptr(perm_idx), _lib.ptr(seed6), _lib.ptr(cdr), C.byref(cfg),
+                                 out.ctypes.data, _lib.ptr(seeds_out), C.byref(st))
+    _lib.check(rc, allow=(_lib.ERR_FIT_FAILED,) if allow_failed else ())
+    if return_seeds:
+        return out, st.as_dict(), seeds_out
+    return out, st.as_dict()
+
+
+def ks(vals, cond01, gene_off, old_pvalue=False):
+    """Two-sample KS per gene: (D, p_unadjusted)."""
+    vals, cond01, gene_off = _prep(vals, cond01, gene_off)
+    ng = gene_off.size - 1
+    D = np.zeros(ng)
+    p = np.zeros(ng)
+    st = Stats()
+    _lib.check(_lib.lib().scdd_ks(vals.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, int(old_pvalue),
+                                  D.ctypes.data, p.ctypes.data, C.byref(st)))
+    return D, p
+
+
+def gene_seeds(seed, ngenes):
+    """L'Ecuyer-CMRG state of every bplapply element for RNGseed = seed (see scdd_rng_gene_seeds)."""
+    out = np.zeros((ngenes, 6), dtype=np.uint32)
+    _lib.check(_lib.lib().scdd_rng_gene_seeds(C.c_uint32(int(seed) & 0xFFFFFFFF), ngenes, out.ctypes.data))
+    return out
+
+
+def sample_perms(state6, n, B):
+    """B draws of sample(1:n) from a L'Ecuyer state (host). Returns (perms[B, n] 1-based, new_state)."""
+    st = np.ascontiguousarray(state6, dtype=np.uint32).copy()
+    out = np.zeros((B, n), dtype=np.int32)
+    _lib.check(_lib.lib().scdd_rng_sample_perms(st.ctypes.data, n, B, out.ctypes.data))
+    return out, st
+
+
+def mt_sample_perms(seed, n, count):
+    """set.seed(seed); replicate(count, sample(1:n)) with R's default Mersenne-Twister (host)."""
+    out = np.zeros((count, n), dtype=np.int32)
+    _lib.check(_lib.lib().scdd_rng_mt_sample_perms(C.c_uint32(int(seed) & 0xFFFFFFFF), n, count, out.ctypes.data))
+    return out
+
+
+class Plan:
+    """Gene block resident in HBM (throughput harness; scdd_plan_* of the C ABI)."""
+
+    def __init__(self, device, logy, cond01, gene_off, chunk_perms, seed6, cfg=None, cdr=None):
+        cfg = cfg or make_cfg()
+        logy, cond01, gene_off = _prep(logy, cond01, gene_off)
+        self.ngenes = gene_off.size - 1
+        self.chunk_perms = int(chunk_perms)
+        seed6 = np.ascontiguousarray(seed6, dtype=np.uint32).reshape(self.ngenes, 6)
+        if cdr is not None:
+            cdr = np.ascontiguousarray(cdr, dtype=np.float64)
+        self._h = _lib.lib().scdd_plan_create(int(device), logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data,
+                                              self.ngenes, C.byref(cfg), self.chunk_perms, seed6.ctypes.data,
+                                              _lib.ptr(cdr))
+        if not self._h:
+            raise ScddError(-3, _lib.last_error())
+
+    def run_chunk(self, stream_ptr=0, nperms=None):
+        _lib.check(_lib.lib().scdd_plan_run_chunk(self._h, C.c_void_p(stream_ptr), int(nperms or self.chunk_perms)))
+
+    def bf_device_ptr(self):
+        return _lib.lib().scdd_plan_bf_device_ptr(self._h)
+
+    def stats(self):
+        st = Stats()
+        _lib.check(_lib.lib().scdd_plan_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        if self._h:
+            _lib.lib().scdd_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

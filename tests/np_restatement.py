@@ -62,6 +62,8 @@ def qclass(x, k):
     n = k
     while q.size < k + 1:
         n += 1
+        if n > 64:  # same bound as the C oracle / the kernels (R itself would keep going)
+            break
         q = r_unique(r_quantile7(xs, r_seq01(n)))
     if q.size > k + 1:
         dq = np.diff(q)
@@ -71,7 +73,7 @@ def qclass(x, k):
     q[0] = xs[0] - eps
     q[-1] = xs[-1] + eps
     cl = np.zeros(x.size, dtype=int)
-    for i in range(k):
+    for i in range(min(k, q.size - 1)):
         cl[(x >= q[i]) & (x < q[i + 1])] = i + 1
     return cl
 

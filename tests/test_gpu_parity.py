@@ -1,0 +1,183 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star):
+  * selected G and cluster assignments identical per gene (near-tie cases counted, must be 0 here)
+  * BIC / log-likelihood / log Bayes factor within 1e-8 relative
+  * permutation p-values identical given identical permutations
+  * KS statistic bit-exact
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from scdd_b200 import hotpath as hp
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+PRIORS = dict(alpha=0.01, mu0=0.0, s0=0.01, a0=0.01, b0=0.01)   # R/scDD.R:203
+
+
+def _load(golden_dir, name, genes=None):
+    d = np.load(os.path.join(golden_dir, name), allow_pickle=True)
+    X, cond = d["normcounts"], d["condition"]
+    if genes is not None:
+        X = X[genes]
+    return X, cond
+
+
+def _check_fits(X, cond):
+    logy, c01, off = hp.gene_csr(X, cond)
+    fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
+    ofits, ocls_oa, ocls_c, obf, oden = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    ng = off.size - 1
+    for g in range(ng):
+        for w in range(3):
+            f, o = fits[g, w], ofits[g][w]
+            assert f["G"] == o["G"], (g, w)
+            assert f["n"] == o["n"] and f["df"] == o["df"]
+            np.testing.assert_allclose(f["bic"], o["bic"], rtol=RTOL)
+            np.testing.assert_allclose(f["loglik"], o["loglik"], rtol=RTOL)
+            np.testing.assert_allclose(f["mean"][:o["G"]], o["mean"], rtol=1e-7)
+            np.testing.assert_allclose(f["var"][:o["G"]], o["var"], rtol=1e-7)
+    assert np.array_equal(cls_oa, ocls_oa)
+    assert np.array_equal(cls_c, ocls_c)
+    np.testing.assert_allclose(bf, obf, rtol=RTOL)
+    np.testing.assert_allclose(den, oden, rtol=RTOL)
+    assert st["iter_cap_hits"] == 0 and st["failed_sets"] == 0
+    return st
+
+
+def test_observed_fits_scDatExSim(golden_dir):
+    X, cond = _load(golden_dir, "scDatExSim.npz")
+    st = _check_fits(X, cond)
+    assert st["fit_sets"] == 3 * X.shape[0]
+
+
+def test_observed_fits_scDatEx(golden_dir):
+    X, cond = _load(golden_dir, "scDatEx.npz")
+    _check_fits(X, cond)
+
+
+def test_observed_work_counters_match_oracle(golden_dir):
+    X, cond = _load(golden_dir, "scDatExSim.npz", genes=slice(0, 4))
+    logy, c01, off = hp.gene_csr(X, cond)
+    _, _, _, _, _, st = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
+    T = P = 0.0
+    for g in range(4):
+        y = logy[off[g]:off[g + 1]]
+        c = c01[off[g]:off[g + 1]]
+        for v in (y, y[c == 0], y[c == 1]):
+            po.fit_table(v)
+            t, p = po.last_work()
+            T += t
+            P += p
+    # identical EM iteration counts => identical work counters
+    assert st["triples"] == T and st["point_iters"] == P
+
+
+@pytest.mark.parametrize("name,ngenes,B", [("scDatExSim.npz", 30, 20), ("scDatEx.npz", 60, 10)])
+def test_perm_bf_host_permutations(golden_dir, name, ngenes, B):
+    """config 2: permutations drawn on the host with R's RNG (sample(1:n)), identical in both arms."""
+    X, cond = _load(golden_dir, name, genes=slice(0, ngenes))
+    logy, c01, off = hp.gene_csr(X, cond)
+    perms = []
+    for g in range(ngenes):
+        n = int(off[g + 1] - off[g])
+        perms.append(hp.mt_sample_perms(1000 + g, n, B).ravel())
+    perms = np.concatenate(perms)
+    out, st = hp.perm_bf(logy, c01, off, B, perm_idx=perms, cfg=hp.make_cfg(**PRIORS))
+    ref = po.perm_batch(logy, c01, off, B, perm_idx=perms, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out, ref, rtol=RTOL)
+    # p-values (R/scDD.R:471-472) identical
+    _, _, _, bf, _, _ = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
+    _, _, _, obf, _ = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    assert np.array_equal((out > bf[:, None]).sum(1), (ref > obf[:, None]).sum(1))
+    assert st["fit_sets"] == 2 * ngenes * B
+
+
+def test_perm_bf_device_permutations_equal_host_drawn(golden_dir):
+    """the device's R sampler (L'Ecuyer-CMRG + rejection) must reproduce the host-drawn permutations"""
+    X, cond = _load(golden_dir, "scDatExSim.npz", genes=slice(0, 12))
+    logy, c01, off = hp.gene_csr(X, cond)
+    B = 7
+    seeds = hp.gene_seeds(2024, 12)
+    out_dev, st, seeds_out = hp.perm_bf(logy, c01, off, B, seed6=seeds, cfg=hp.make_cfg(**PRIORS), return_seeds=True)
+    perms, states = [], []
+    for g in range(12):
+        p, s = hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), B)
+        perms.append(p.ravel())
+        states.append(s)
+    out_host, _ = hp.perm_bf(logy, c01, off, B, perm_idx=np.concatenate(perms), cfg=hp.make_cfg(**PRIORS))
+    assert np.array_equal(out_dev, out_host)
+    assert np.array_equal(seeds_out, np.array(states))
+    ref = po.perm_batch(logy, c01, off, B, seed6=seeds, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out_dev, ref, rtol=RTOL)
+
+
+def test_perm_bf_adjusted_cdr(golden_dir):
+    """adjust.perms = TRUE: residual permutation with the CDR covariate, 3 fit-sets per permutation"""
+    X, cond = _load(golden_dir, "scDatExSim.npz", genes=slice(0, 10))
+    logy, c01, off = hp.gene_csr(X, cond)
+    Xall, _ = _load(golden_dir, "scDatExSim.npz")
+    C = (Xall > 0).sum(axis=0) / Xall.shape[0]                      # R/scDD.R:457
+    cdr = np.broadcast_to(C, X.shape)[X > 0]
+    B = 6
+    seeds = hp.gene_seeds(5, 10)
+    out, st = hp.perm_bf(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS))
+    ref = po.perm_batch(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-7)
+    assert st["fit_sets"] == 3 * 10 * B
+
+
+@pytest.mark.parametrize("name", ["scDatExSim.npz", "scDatEx.npz"])
+@pytest.mark.parametrize("incl_zero", [False, True])
+def test_ks_bit_exact(golden_dir, name, incl_zero):
+    X, cond = _load(golden_dir, name)
+    vals, c01, off = hp.gene_csr(X, cond, log=False, incl_zero=incl_zero)
+    D, p = hp.ks(vals, c01, off)
+    oD, op = po.ks_batch(vals, c01, off)
+    assert np.array_equal(D, oD)          # bit-exact statistic
+    assert np.array_equal(p, op)          # same series evaluated with the same libm on the host
+
+
+def test_ks_with_ties_and_ragged():
+    rng = np.random.default_rng(3)
+    rows, conds = [], []
+    for n in (2, 3, 17, 64, 65, 500, 1025):
+        v = np.round(rng.gamma(2.0, 2.0, size=n), 1) + 0.1
+        c = (rng.random(n) < 0.4).astype(np.int32)
+        c[0], c[-1] = 0, 1
+        rows.append(v)
+        conds.append(c)
+    off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.int64)
+    vals, c01 = np.concatenate(rows), np.concatenate(conds)
+    D, p = hp.ks(vals, c01, off)
+    oD, op = po.ks_batch(vals, c01, off)
+    assert np.array_equal(D, oD) and np.array_equal(p, op)
+
+
+def test_synthetic_bimodal_and_small_genes():
+    """edge cases: tiny n (G > n rows), strongly bimodal, heavy ties"""
+    rng = np.random.default_rng(11)
+    rows, conds = [], []
+    for n in (6, 7, 9, 12, 40, 150, 600):
+        a = rng.normal(1.0, 0.4, size=n // 2)
+        b = rng.normal(5.0, 0.6, size=n - n // 2)
+        rows.append(np.concatenate([a, b]))
+        conds.append((np.arange(n) % 2).astype(np.int32))
+    # ties: values on a coarse grid
+    rows.append(np.round(rng.normal(3.0, 1.0, size=80), 1))
+    conds.append((np.arange(80) % 2).astype(np.int32))
+    off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.int64)
+    logy, c01 = np.concatenate(rows), np.concatenate(conds)
+    fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS), allow_failed=True)
+    ofits, ocls_oa, ocls_c, obf, oden = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    for g in range(off.size - 1):
+        for w in range(3):
+            assert fits[g, w]["G"] == ofits[g][w]["G"], (g, w)
+            np.testing.assert_allclose(fits[g, w]["bic"], ofits[g][w]["bic"], rtol=RTOL)
+    assert np.array_equal(cls_oa, ocls_oa) and np.array_equal(cls_c, ocls_c)
+    np.testing.assert_allclose(bf, obf, rtol=RTOL)
+    np.testing.assert_allclose(den, oden, rtol=RTOL)
