@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's R interface for the accelerated path.
+
+R is not available in the build image, so the reference-facing layer is mirrored in Python with the SAME
+names, argument meaning, error strings and result columns as the R functions it stands in for:
+
+    scDD()      R/scDD.R:217-602     (dispatch only: filters, observed fits, permutations / KS, p-values,
+                                      cluster counts, Zhat matrices, Genes table)
+    testKS()    R/Test_KS.R:55-83
+    results()   R/helper.R:62-66
+
+All numerical work of the hot path happens in libscdd_b200.so (CUDA); this module contains no fitting code.
+What stays in R in a real deployment and is therefore NOT reproduced here (out of scope /
+"next"): classifyDD and feDP (DDcategory labels of individual genes; they consume R's RNG via rt/runif) and
+testZeroes (arm::bayesglm).  `DDcategory` is therefore "NS" for non-significant genes and None (NA) for
+significant ones; the R shim in r/ keeps calling the reference's own classifyDD / feDP on the lists this
+path produces.
+"""
+import numpy as np
+
+from . import hotpath as hp
+
+
+class SingleCellExperiment:
+    """Minimal stand-in for Bioconductor's SingleCellExperiment: assays, colData, metadata, dimnames."""
+
+    def __init__(self, assays, colData, rownames=None, colnames=None):
+        self.assays = {k: np.asarray(v, dtype=np.float64) for k, v in assays.items()}
+        self.colData = {k: np.asarray(v) for k, v in colData.items()}
+        first = next(iter(self.assays.values())) if self.assays else np.zeros((0, 0))
+        self.rownames = list(rownames) if rownames is not None else [f"gene{i + 1}" for i in range(first.shape[0])]
+        self.colnames = list(colnames) if colnames is not None else [f"Sample{i + 1}" for i in range(first.shape[1])]
+        self.metadata = {}
+
+    def assayNames(self):
+        return list(self.assays.keys())
+
+
+def normcounts(sce):
+    return sce.assays["normcounts"]
+
+
+def p_adjust_BH(p):
+    """stats::p.adjust(p, method = "BH") with NA handling (NaN kept, n = number of non-NA)."""
+    p = np.asarray(p, dtype=np.float64)
+    out = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pv = p[ok]
+    n = pv.size
+    if n == 0:
+        return out
+    o = np.argsort(-pv, kind="stable")           # order(p, decreasing = TRUE)
+    ro = np.argsort(o, kind="stable")
+    adj = np.minimum(1.0, np.minimum.accumulate(n / np.arange(n, 0, -1) * pv[o]))
+    out[ok] = adj[ro]
+    return out
+
+
+def _unique_in_order(x):
+    seen, out = set(), []
+    for v in x.tolist():
+        if v not in seen:
+            seen.add(v)
+            out.append(v)
+    return out
+
+
+def luOutlier(x, min_size=3):
+    """R/Cluster_actions.R:25  sum(table(x) >= min.size)"""
+    _, cnt = np.unique(np.asarray(x), return_counts=True)
+    return int((cnt >= min_size).sum())
+
+
+def testKS(dat, condition, inclZero=True, numDE=None, DEIndex=None, rownames=None):
+    """R/Test_KS.R:55-83.  dat: genes x cells matrix.  Returns dict(genes, p, p.unadj[, power, fdr])."""
+    dat = np.asarray(dat, dtype=np.float64)
+    condition = np.asarray(condition)
+    lev = _unique_in_order(condition)
+    keep = (condition == lev[0]) | (condition == lev[1])   # x1 / x2 use the first two levels only
+    vals, c01, off = hp.gene_csr(dat[:, keep], condition[keep], ref=lev[0], log=False, incl_zero=bool(inclZero))
+    _, p_unadj = hp.ks(vals, c01, off)
+    p_adj = p_adjust_BH(p_unadj)
+    sig = np.nonzero(p_adj < 0.05)[0]                      # hard-coded 0.05, R/Test_KS.R:71
+    names = rownames if rownames is not None else [str(i + 1) for i in range(dat.shape[0])]
+    out = {"genes": {names[i]: int(i + 1) for i in sig}, "p": p_adj, "p.unadj": p_unadj}
+    if numDE is not None:
+        de = set(int(i) for i in np.asarray(DEIndex).tolist())
+        sig1 = [int(i + 1) for i in sig]
+        out["power"] = sum(1 for i in sig1 if i in de) / numDE
+        out["fdr"] = (sum(1 for i in sig1 if i not in de) / len(sig1)) if sig1 else float("nan")
+    return out
+
+
+def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=False, param=None,
+         parallelBy=("Genes", "Permutations"), condition="condition", min_size=3, min_nonzero=None, level=0.05,
+         categorize=True, perm_source="device", verbose=True):
+    """R/scDD.R:217-602 with the per-gene work done on the GPU.
+
+    param:       stands in for the BiocParallel param: dict(RNGseed=int[, devices=[...]]) -- RNGseed seeds the
+                 per-gene L'Ecuyer-CMRG streams exactly as bplapply would.
+    perm_source: "device" draws the permutations on the GPU (bit-exact R sampler); "host" draws them with the
+                 library's host implementation of the same sampler and ships the indices (configs 1-2).
+    """
+    msg = (lambda s: print(s)) if verbose else (lambda s: None)
+    if prior_param is None:
+        prior_param = dict(alpha=0.10, mu0=0, s0=0.01, a0=0.01, b0=0.01)
+    if not isinstance(SCdat, SingleCellExperiment):
+        raise ValueError("Please provide a valid 'SingleCellExperiment' object.")
+    if not SCdat.assayNames() or "normcounts" not in SCdat.assayNames():
+        raise ValueError("Please make sure the 'SingleCellExperiment' object includes an assays slot named "
+                         "'normcounts' that contains normalized counts on the original scale")
+    if (not categorize) and permutations != 0:
+        raise ValueError("Categorization will be carried out if permuations are run.")
+    if isinstance(parallelBy, (tuple, list)):
+        parallelBy = parallelBy[0]
+    if parallelBy not in ("Genes", "Permutations"):
+        raise ValueError("'arg' should be one of 'Genes', 'Permutations'")
+    if testZeroes:
+        raise NotImplementedError("testZeroes=TRUE needs arm::bayesglm (out of scope of the accelerated path, "
+                                  "SURVEY section 2); the benchmark configs use testZeroes=FALSE")
+    X = normcounts(SCdat)
+    cond = SCdat.colData.get(condition)
+    if cond is None or len(_unique_in_order(cond)) != 2 or len(cond) != X.shape[1]:
+        raise ValueError("Error: Please specify valid condition labels.")
+    ref = _unique_in_order(cond)[0]
+    if (X < 0).sum() > 0:
+        raise ValueError("Error: Negative values for Normalized Expression counts detected. "
+                         "Please ensure all counts are non-negative")
+    if min_nonzero is None:
+        min_nonzero = min_size
+    isref = cond == ref
+    need = max(min_size, 2, min_nonzero)
+    tofit = np.nonzero(((X[:, isref] > 0).sum(1) >= need) & ((X[:, ~isref] > 0).sum(1) >= need))[0]
+    ngenes = X.shape[0]
+    if tofit.size < ngenes:
+        msg(f"Notice: {ngenes - tofit.size} genes have less than {min_nonzero} nonzero cells per condition.  "
+            f"Skipping these genes.")
+    # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310)
+    def _const(rows):
+        out = np.zeros(rows.shape[0], dtype=bool)
+        for i, r in enumerate(rows):
+            nzv = r[r > 0]
+            out[i] = np.unique(nzv).size == 1
+        return out
+    skip = _const(X[np.ix_(tofit, np.nonzero(isref)[0])]) | _const(X[np.ix_(tofit, np.nonzero(~isref)[0])])
+    if skip.any():
+        msg(f"Notice: {int(skip.sum())} Genes have constant nonzero values.  Skipping these genes.")
+        tofit = tofit[~skip]
+    param = dict(param or {})
+    if param.get("devices") is not None:
+        hp.set_devices(param["devices"])
+    msg(f"Setting up parallel back-end using {hp.device_count()} GPUs")
+    cfg = hp.make_cfg(alpha=prior_param["alpha"], mu0=prior_param["mu0"], s0=prior_param["s0"], a0=prior_param["a0"],
+                      b0=prior_param["b0"], min_size=min_size)
+    Xf = X[tofit]
+    logy, c01, off = hp.gene_csr(Xf, cond, ref=ref)
+    nf = tofit.size
+    stats = {}
+    if categorize:
+        msg("Clustering observed expression data for each gene")
+    fits = cls_oa = cls_c = None
+    bf = den = None
+    comps_all = comps_c1 = comps_c2 = np.full(nf, np.nan)
+    if categorize:
+        fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=cfg, with_bf=permutations != 0)
+        stats["observed"] = st
+        comps_all, comps_c1, comps_c2 = np.zeros(nf), np.zeros(nf), np.zeros(nf)
+        for g in range(nf):
+            s = slice(off[g], off[g + 1])
+            c = c01[s]
+            comps_all[g] = luOutlier(cls_oa[s], min_size)
+            comps_c1[g] = luOutlier(cls_c[s][c == 0], min_size)
+            comps_c2[g] = luOutlier(cls_c[s][c == 1], min_size)
+    if permutations == 0:
+        msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
+            "in distributions instead of the Bayes Factor permutation test")
+        res_ks = testKS(Xf, cond, inclZero=False)
+        sig = np.nonzero(res_ks["p"] < level)[0]
+        pvals = res_ks["p.unadj"]
+    else:
+        msg("Performing permutations to evaluate independence of clustering and condition for each gene")
+        msg(f"Parallelizing by {parallelBy}")
+        seed = int(param.get("RNGseed", 1))
+        seeds = hp.gene_seeds(seed, nf)
+        cdr = None
+        if adjust_perms:
+            C = (Xf > 0).sum(axis=0) / float(nf)                       # R/scDD.R:457
+            cdr = np.broadcast_to(C, Xf.shape)[Xf > 0]
+        if perm_source == "host":
+            perm_idx = np.concatenate([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), permutations)[0].ravel()
+                                       for g in range(nf)]) if nf else np.zeros(0, dtype=np.int32)
+            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, perm_idx=perm_idx, cdr=cdr, cfg=cfg)
+        else:
+            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, seed6=seeds, cdr=cdr, cfg=cfg)
+        stats["permutations"] = st
+        obs = (bf - den) if adjust_perms else bf                      # R/scDD.R:467-473
+        pvals = (bf_perm > obs[:, None]).sum(axis=1) / float(permutations)
+        sig = np.nonzero(p_adjust_BH(pvals) < level)[0]
+    pvals_all = np.full(ngenes, np.nan)
+    pvals_all[tofit] = pvals
+    cats_all = [None] * ngenes
+    if categorize:
+        msg("Classifying significant genes into patterns")
+        sigset = set(sig.tolist())
+        for j, g in enumerate(tofit):
+            cats_all[g] = None if j in sigset else "NS"   # DE/DP/DM/DB/NC labels come from R's classifyDD / feDP
+    # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label
+    if categorize:
+        MAP = np.ones(X.shape)
+        MAP[X == 0] = 0
+        rows = np.repeat(tofit, np.diff(off))
+        cols = np.nonzero(Xf > 0)[1]
+        MAP[rows, cols] = cls_oa
+        MAPc = np.ones(X.shape)
+        MAPc[X == 0] = 0
+        MAPc[rows, cols] = cls_c
+        MAP1, MAP2 = MAPc[:, isref], MAPc[:, ~isref]
+    else:
+        MAP1 = MAP2 = MAP = "Categorize set to FALSE; no clustering provided."
+
+    def _spread(v):
+        out = np.full(ngenes, np.nan)
+        out[tofit] = v
+        return out
+    Genes = {"gene": list(SCdat.rownames), "DDcategory": cats_all,
+             "Clusters.combined": _spread(comps_all), "Clusters.c1": _spread(comps_c1),
+             "Clusters.c2": _spread(comps_c2), "nonzero.pvalue": pvals_all,
+             "nonzero.pvalue.adj": p_adjust_BH(pvals_all)}
+    SCdat.metadata["Genes"] = Genes
+    SCdat.metadata["Zhat.combined"] = MAP
+    SCdat.metadata["Zhat.c1"] = MAP1
+    SCdat.metadata["Zhat.c2"] = MAP2
+    SCdat.metadata["_scdd_b200"] = {"stats": stats, "tofit": tofit, "fits": fits, "bf": bf, "den": den}
+    return SCdat
+
+
+def results(SCdat, type="Genes"):
+    """R/helper.R:62-66"""
+    if type not in ("Genes", "Zhat.c1", "Zhat.c2", "Zhat.combined"):
+        raise ValueError("'arg' should be one of 'Genes', 'Zhat.c1', 'Zhat.c2', 'Zhat.combined'")
+    return SCdat.metadata[type]

@@ -1,0 +1,101 @@
+"""CPU checks of libscdd_b200.so: it loads, exports every symbol include/scdd_b200.h declares, fails loudly
+without a GPU, and its host-side pieces (x87 emulation, exp, R RNG) are right.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from scdd_b200 import _lib, hotpath as hp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "scdd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(scdd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.lib()
+    names = _declared()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib.EXPORTS) == names
+    assert L.scdd_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.Cfg) == 5 * 8 + 4 * 4
+    assert C.sizeof(_lib.Fit) == 4 * 4 + 2 * 8 + 2 * 5 * 8 == _lib.FIT_DTYPE.itemsize
+    assert C.sizeof(_lib.Stats) == 15 * 8
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    y = np.log(np.arange(1, 21, dtype=np.float64))
+    c = (np.arange(20) % 2).astype(np.int32)
+    off = np.array([0, 20], dtype=np.int64)
+    for call in (lambda: hp.fit_observed(y, c, off), lambda: hp.perm_bf(y, c, off, 2, seed6=hp.gene_seeds(1, 1)),
+                 lambda: hp.ks(y, c, off)):
+        with pytest.raises(hp.ScddError) as e:
+            call()
+        assert e.value.code == -1 and "no CPU fallback" in str(e.value)
+
+
+def test_x87_cumsum_emulation_is_bit_exact():
+    """the KS kernel's software extended-precision accumulator vs the hardware's long double"""
+    rng = np.random.default_rng(0)
+    L = _lib.lib()
+    cases = []
+    for nx, ny in [(100, 100), (78, 64), (997, 1003), (3, 7), (1, 1), (25000, 24999)]:
+        cases.append(np.where(rng.random(nx + ny) < nx / (nx + ny), 1.0 / nx, -1.0 / ny))
+    cases.append(rng.normal(size=4000) * 10.0 ** rng.integers(-15, 15, size=4000))
+    cases.append(np.array([1.0, -1.0, 1e-300, 3.0, -3.0, 0.0, -0.0, 2.5e-300]))   # normal-range doubles only (KS sums of +-1/n)
+    for steps in cases:
+        steps = np.ascontiguousarray(steps, dtype=np.float64)
+        out = np.zeros_like(steps)
+        L.scdd_selftest_x87_cumsum(steps.ctypes.data, steps.size, out.ctypes.data)
+        ref = np.cumsum(steps.astype(np.longdouble)).astype(np.float64)
+        assert np.array_equal(out, ref)
+
+
+def test_kernel_exp_accuracy():
+    rng = np.random.default_rng(1)
+    x = -rng.random(200000) * 708.0
+    x[:4] = [0.0, -708.0, -1e-300, -0.5]
+    out = np.zeros_like(x)
+    _lib.lib().scdd_selftest_exp(x.ctypes.data, x.size, out.ctypes.data)
+    ref = np.exp(x.astype(np.longdouble))
+    rel = np.abs((out.astype(np.longdouble) - ref) / ref)
+    assert float(rel.max()) < 2.3e-16      # < 1.05 ulp
+    assert out[0] == 1.0
+
+
+def test_r_rng_host_matches_oracle_and_known_answers():
+    # R >= 3.6: set.seed(1); sample(1:10)  /  set.seed(42); sample(1:10)
+    assert hp.mt_sample_perms(1, 10, 1)[0].tolist() == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
+    assert hp.mt_sample_perms(42, 10, 1)[0].tolist() == [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]
+    seeds = hp.gene_seeds(7, 3)
+    r = po.RRng(seed=7, kind="lecuyer")
+    assert np.array_equal(seeds[0], r.lecuyer_state())
+    assert np.array_equal(seeds[1], po.lecuyer_next_substream(seeds[0]))
+    assert np.array_equal(seeds[2], po.lecuyer_next_substream(seeds[1]))
+    for n in (1, 2, 17, 142, 2000):
+        perms, st = hp.sample_perms(seeds[1], n, 3)
+        ro = po.RRng(state6=seeds[1])
+        ref = np.stack([ro.sample(n) for _ in range(3)])
+        assert np.array_equal(perms, ref)
+        assert np.array_equal(st, ro.lecuyer_state())
+
+
+def test_mt_stream_continues_across_draws():
+    a = hp.mt_sample_perms(5, 50, 4)
+    r = po.RRng(seed=5, kind="mt")
+    assert np.array_equal(a, np.stack([r.sample(50) for _ in range(4)]))
