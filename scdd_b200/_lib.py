@@ -69,7 +69,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.build()
+    path = os.environ.get("SCDD_LIB_OVERRIDE") or _build.build()   # override: A/B testing of kernel builds
     L = C.CDLL(path)
     dp, ip, lp, up = (C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint32))
     vp = C.c_void_p

@@ -161,41 +161,167 @@ __device__ __noinline__ int qclass_breaks(const double* xs, int n, int k, double
 }
 
 // ---------------------------------------------------------------------------------------------
-// E-step for one point: unnormalised responsibilities e_k = exp(t_k - max t), their sum S and the max.
-// Written with explicit rounding intrinsics so every inlined copy performs identical arithmetic.
+// E-step arithmetic for N = (points x components) independent arguments at once.
+// exp() is evaluated "column-wise": every step of the range reduction and of the Horner chain is issued
+// for all N arguments before the next step, so the in-order warp always has N independent DFMAs in
+// flight (ptxas keeps each scalar exp() as one serial dependency chain otherwise).
+// Every element goes through exactly the operation sequence of exp_neg() (device_math.cuh).
 // ---------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ void estep_point(double x, const double (&mu)[G], const double (&nh)[G],
-                                            const double (&lc)[G], double (&e)[G], double (&d)[G],
-                                            double (&q)[G], double& S, double& tmax) {
-    double t[G];
+__device__ const double EXP_TABLE_GLOBAL[32] = SCDD_EXP_TABLE_INIT;
+// polynomial coefficients of the table-free exp (expp::C): constant-bank operands, fetched with LDCU.128
+__constant__ double EXP_RED[3] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+__constant__ double EXP_TAB_CONST[7] = {46.16624130844683, -0.021660849392446835, -5.145609244655338e-14,
+                                        1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+__constant__ double EXP_POLY[10] = {
+    2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05,
+    0.00019841269863053618, 0.0013888888917213717, 0.008333333333330062, 0.04166666666662413,
+    0.16666666666666669, 0.5000000000000001};   // source of the per-CTA shared copy
+
+// 1/S for S in [1, GMAX]: MUFU.RCP64H seed + two Newton steps (5 DFMA, <= 1 ulp).  No special-case
+// branch: the argument range is known, unlike for the general-purpose __drcp_rn.
+__device__ __forceinline__ double rcp_sum(double x) {
+#ifndef SCDD_FAST_RCP
+#define SCDD_FAST_RCP 1
+#endif
+#if SCDD_FAST_RCP
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return __drcp_rn(x);
+#endif
+}
+
+// exp() arguments below mclust's SMALOG = -708 give exactly 0 (as in the reference).  The test is made on
+// the high word (a <= 0 here) so that no fp64-pipe instruction is spent on it, and applied to the
+// result so that it stays off the dependency chain of the polynomial.
+__device__ __forceinline__ double zero_if_small(double a, int hi, int lo) {
+    const bool small = (unsigned)__double2hiint(a) > 0xC0862000u;
+    return __hiloint2double(small ? 0 : hi, small ? 0 : lo);
+}
+
+template <int N>
+__device__ __forceinline__ void exp_neg_vec(const double (&a)[N], double (&e)[N], const double* tab) {
+    double t[N], r[N], p[N];
+#if SCDD_EXP_TABLE
+    using namespace expc;
 #pragma unroll
-    for (int k = 0; k < G; k++) {
-        d[k] = __dsub_rn(x, mu[k]);
-        q[k] = __dmul_rn(d[k], d[k]);
-        t[k] = fma(q[k], nh[k], lc[k]);
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_TAB_CONST[1], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_TAB_CONST[2], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[3], r[i], EXP_TAB_CONST[4]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[5]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[6]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], C2);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = p[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int n = __double2loint(t[i]);
+        const double T = tab[n & 31];
+        const double v = fma(T, p[i], T);
+        e[i] = zero_if_small(a[i], __double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
     }
-    tmax = t[0];
+#else
+    using namespace expp;
+    const double MAGIC = expc::MAGIC;
 #pragma unroll
-    for (int k = 1; k < G; k++) tmax = fmax(tmax, t[k]);
-    S = 0.0;
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_RED[0], MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_RED[1], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_RED[2], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_POLY[0], r[i], EXP_POLY[1]);
+#pragma unroll
+    for (int j = 2; j < 10; j++) {
+#pragma unroll
+        for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_POLY[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        e[i] = zero_if_small(a[i], __double2hiint(p[i]) + (__double2loint(t[i]) << 20), __double2loint(p[i]));
+#endif
+}
+
+// Component parameters in E-step form: mu_k, nh_k = -1/(2 sigsq_k), lc_k = log pro_k - (log 2 pi + log sigsq_k)/2.
+// ParamsReg keeps them in registers (3G doubles per lane); ParamsSmem re-reads them from the warp's
+// shared-memory block for every point (broadcast loads on the LSU pipe), which frees 6G registers for
+// the interleaved exp() chains -- the fp64 pipe, not the LSU, is the bottleneck of this kernel.
+template <int G>
+struct ParamsReg {
+    const double* tab;   // 2^(j/32) table
+    double mu[G], nh[G], lc[G];
+    __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
+};
+struct ParamsSmem {
+    const double* tab;   // 2^(j/32) table (shared memory)
+    unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
+    __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(l) : "r"(addr + 32u * k + 16u));
+    }
+};
+
+// U points x G components: unnormalised responsibilities e = exp(t - max t), d = x - mu, q = d^2,
+// per point S = sum_k e and the max.
+template <int G, int U, class P>
+__device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
+                                             double (&q)[U * G], double (&S)[U], double (&tmax)[U]) {
+    double a[U * G];
 #pragma unroll
     for (int k = 0; k < G; k++) {
-        double a = __dsub_rn(t[k], tmax);
-        double ek = exp_neg(a);
-        ek = (a >= SMALOG) ? ek : 0.0;
-        e[k] = ek;
-        S = __dadd_rn(S, ek);
+        double m, h, l;
+        prm.get(k, m, h, l);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            d[u * G + k] = __dsub_rn(x[u], m);
+            q[u * G + k] = __dmul_rn(d[u * G + k], d[u * G + k]);
+            a[u * G + k] = fma(q[u * G + k], h, l);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double m = a[u * G];
+#pragma unroll
+        for (int k = 1; k < G; k++) m = (a[u * G + k] > m) ? a[u * G + k] : m;
+        tmax[u] = m;
+#pragma unroll
+        for (int k = 0; k < G; k++) a[u * G + k] = __dsub_rn(a[u * G + k], m);
+    }
+    exp_neg_vec<U * G>(a, e, prm.tab);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double s = e[u * G];
+#pragma unroll
+        for (int k = 1; k < G; k++) s = __dadd_rn(s, e[u * G + k]);
+        S[u] = s;
     }
 }
 
 // map(z): first index of the row maximum of z = e / S
-template <int G>
-__device__ __forceinline__ int map_label(double x, const double (&mu)[G], const double (&nh)[G],
-                                         const double (&lc)[G]) {
-    double e[G], d[G], q[G], S, tmax;
-    estep_point<G>(x, mu, nh, lc, e, d, q, S, tmax);
-    double rs = __drcp_rn(S);
+template <int G, class P>
+__device__ __forceinline__ int map_label(double x, const P& prm) {
+    double xx[1] = {x};
+    double e[G], d[G], q[G], S[1], tmax[1];
+    estep_points<G, 1, P>(xx, prm, e, d, q, S, tmax);
+    double rs = rcp_sum(S[0]);
     double best = __dmul_rn(e[0], rs);
     int bk = 0;
 #pragma unroll
@@ -207,186 +333,295 @@ __device__ __forceinline__ int map_label(double x, const double (&mu)[G], const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// G >= 2 row: qclass start, EM (mclust me1v semantics: M-step first, stop when the relative change of
-// the log-likelihood is <= 1e-5), BIC, extra M-step, MAP label statistics.
+// Transposing warp reduction: every lane contributes 16 partial sums; afterwards lane L holds the
+// warp total of slot (L >> 1).  16 + 8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5 butterflies.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double reduce16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int h = 8 >> s, off = 16 >> s;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < h; j++) {
+            double send = up ? v[j] : v[j + h];
+            double keep = up ? v[j + h] : v[j];
+            v[j] = keep + __shfl_xor_sync(FULLMASK, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(FULLMASK, v[0], 1);
+}
+__device__ __forceinline__ double slot(double t, int e) { return __shfl_sync(FULLMASK, t, 2 * e); }
+
+// ---------------------------------------------------------------------------------------------
+// E-step over the warp's points fused with the sufficient statistics of the next M-step.
+// Component k's parameters live in lane k ("owner lane"); they are broadcast into registers here.
+// Per-lane partial sums go to v: [0,G) sum z, [G,2G) sum z d, [2G,3G) sum z d^2, [3G] log-likelihood.
 //
 // M-step form: with d = x - mu_old and q = d^2 already needed by the E-step, the new parameters are
 //   mu = mu_old + S(z d)/S(z),  sigsq = S(z q)/S(z) - (S(z d)/S(z))^2
 // which equals mclust's two-pass update in exact arithmetic and needs no stored z matrix.
 // ---------------------------------------------------------------------------------------------
+template <int G, int U, class P>
+__device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
+                                                  double (&C)[G], double& pl, double& hl) {
+    double e[U * G], d[U * G], q[U * G], S[U], tmax[U];
+    estep_points<G, U, P>(x, prm, e, d, q, S, tmax);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double rs = rcp_sum(S[u]);
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            double z = __dmul_rn(e[u * G + k], rs);
+            A[k] += z;
+            B[k] = fma(z, d[u * G + k], B[k]);
+            C[k] = fma(z, q[u * G + k], C[k]);
+        }
+        pl *= S[u];      // sum_i log S_i is taken as the log of a running product (S in [1, G])
+        hl += tmax[u];
+    }
+}
+
+#ifndef SCDD_PARAMS_SMEM
+#define SCDD_PARAMS_SMEM 1
+#endif
+
 template <int G>
-__device__ __noinline__ void fit_row(const double* xs, int n, int lane, Row* row, WarpStats& st,
-                                     int extra_mstep) {
+__device__ __forceinline__ auto load_params(const double* pm, const double* tab) {
+#if SCDD_PARAMS_SMEM
+    ParamsSmem p;
+    p.tab = tab;
+    p.addr = (unsigned)__cvta_generic_to_shared(pm);
+    return p;
+#else
+    ParamsReg<G> p;
+    p.tab = tab;
+#pragma unroll
+    for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
+    return p;
+#endif
+}
+
+template <int G, int U>
+__device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
+                                           const double* tab, double (&v)[16]) {
+    const auto prm = load_params<G>(pm, tab);
+    double A[G], B[G], C[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
+    double hl = 0.0;
+    constexpr int CHUNK = 256 * 32;   // the running product is flushed every 256 points per lane (5^256 < DBL_MAX)
+#pragma unroll 1
+    for (int base = 0; base < n; base += CHUNK) {
+        const int stop = (n - base < CHUNK) ? n : base + CHUNK;
+        double pl = 1.0;
+        int i = base + lane;
+#pragma unroll 1
+        for (; i + 32 * (U - 1) < stop; i += 32 * U) {
+            double x[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) x[u] = xs[i + 32 * u];
+            accumulate_points<G, U>(x, prm, A, B, C, pl, hl);
+        }
+        if (U > 1) {
+#pragma unroll 1
+            for (; i < stop; i += 32) {
+                double x[1] = {xs[i]};
+                accumulate_points<G, 1>(x, prm, A, B, C, pl, hl);
+            }
+        }
+        hl += log(pl);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < G; k++) { v[k] = A[k]; v[G + k] = B[k]; v[2 * G + k] = C[k]; }
+    v[3 * G] = hl;
+}
+
+// MAP labels of the final z and their statistics: v[0,G) count, [G,2G) sum y, [2G,3G) sum y^2
+template <int G>
+__device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
+                                           const double* tab, double (&v)[16]) {
+    const auto prm = load_params<G>(pm, tab);
+    double cnt[G], sy[G], syy[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) { cnt[k] = 0.0; sy[k] = 0.0; syy[k] = 0.0; }
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        double x = xs[i];
+        int bk = map_label<G>(x, prm);
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            if (k == bk) { cnt[k] += 1.0; sy[k] += x; syy[k] = fma(x, x, syy[k]); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < G; k++) { v[k] = cnt[k]; v[G + k] = sy[k]; v[2 * G + k] = syy[k]; }
+}
+
+// unroll factor of the point loop: small G has little instruction-level parallelism per point
+#ifndef SCDD_UNROLL_MAXG
+#define SCDD_UNROLL_MAXG 2
+#endif
+template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_MAXG) ? 2 : 1; };
+
+__device__ __noinline__ void estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
+                                            const double* tab, double (&v)[16]) {
+    switch (G) {
+        case 2: estep_pass<2, Unroll<2>::value>(xs, n, lane, pm, tab, v); break;
+        case 3: estep_pass<3, Unroll<3>::value>(xs, n, lane, pm, tab, v); break;
+        case 4: estep_pass<4, Unroll<4>::value>(xs, n, lane, pm, tab, v); break;
+        default: estep_pass<5, Unroll<5>::value>(xs, n, lane, pm, tab, v); break;
+    }
+}
+
+__device__ __noinline__ void label_dispatch(int G, const double* xs, int n, int lane, const double* pm,
+                                            const double* tab, double (&v)[16]) {
+    switch (G) {
+        case 2: label_pass<2>(xs, n, lane, pm, tab, v); break;
+        case 3: label_pass<3>(xs, n, lane, pm, tab, v); break;
+        case 4: label_pass<4>(xs, n, lane, pm, tab, v); break;
+        default: label_pass<5>(xs, n, lane, pm, tab, v); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// G >= 2 row: qclass start, EM (mclust me1v semantics: M-step first, stop when the relative change of
+// the log-likelihood is <= 1e-5), BIC, extra M-step, MAP label statistics.
+// One copy of this code serves every G: the scalar M-step runs once per warp with lane k owning
+// component k (lanes >= G shadow component 0), only the point loops are specialised on G.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
+                                     double* pm, const double* tab, int extra_mstep) {
     const double eps = DBL_EPSILON, rteps = 1.4901161193847656e-08, tol = 1e-5;
     const double dn = (double)n;
     if (lane == 0) { row->valid = 0; row->iters = 0; }
     if (G > n) return;   // mclustBIC: G <- G[G <= n]
+    const int kown = lane < G ? lane : 0;
+    const bool owner = lane < G;
 
     double br[GMAX];
-    int nbr = qclass_breaks(xs, n, G, br);
+    const int nbr = qclass_breaks(xs, n, G, br);
+    double b0 = nbr > 0 ? br[0] : INFINITY, b1 = nbr > 1 ? br[1] : INFINITY;
+    double b2 = nbr > 2 ? br[2] : INFINITY, b3 = nbr > 3 ? br[3] : INFINITY;
 
     // ---- first M-step from the hard quantile classes (z = unmap(qclass)) ----
-    double mu[G], sig[G], pro[G], nh[G], lc[G];
+    double mu_own, sig_own, pro_own;
     {
-        double acc[2 * G];
+        double v[16];
 #pragma unroll
-        for (int k = 0; k < 2 * G; k++) acc[k] = 0.0;
+        for (int k = 0; k < 16; k++) v[k] = 0.0;
         for (int i = lane; i < n; i += 32) {
             double x = xs[i];
-            int cl = 0;
-            for (int c = 0; c < nbr; c++) cl += (x >= br[c]) ? 1 : 0;
+            int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
 #pragma unroll
-            for (int k = 0; k < G; k++) {
-                if (k == cl) { acc[k] += 1.0; acc[G + k] += x; }
+            for (int k = 0; k < GMAX; k++) {
+                if (k == cl) { v[k] += 1.0; v[GMAX + k] += x; }
             }
         }
-        warp_sum_vec<2 * G>(acc);
-        double cmin = acc[0];
+        double t = reduce16(v, lane);
+        double cnt = slot(t, kown), sx = slot(t, GMAX + kown);
+        if (__any_sync(FULLMASK, owner && cnt <= rteps)) return;   // an empty class: "mixing proportion fell below threshold"
+        mu_own = sx / cnt;
+        pro_own = cnt / dn;
+        double m0 = __shfl_sync(FULLMASK, mu_own, 0), m1 = __shfl_sync(FULLMASK, mu_own, 1);
+        double m2 = __shfl_sync(FULLMASK, mu_own, 2), m3 = __shfl_sync(FULLMASK, mu_own, 3);
+        double m4 = __shfl_sync(FULLMASK, mu_own, 4);
 #pragma unroll
-        for (int k = 1; k < G; k++) cmin = fmin(cmin, acc[k]);
-        if (cmin <= rteps) return;   // an empty class: "mixing proportion fell below threshold"
-        double ss[G];
-#pragma unroll
-        for (int k = 0; k < G; k++) { mu[k] = acc[G + k] / acc[k]; pro[k] = acc[k] / dn; ss[k] = 0.0; }
+        for (int k = 0; k < 16; k++) v[k] = 0.0;
         for (int i = lane; i < n; i += 32) {
             double x = xs[i];
-            int cl = 0;
-            for (int c = 0; c < nbr; c++) cl += (x >= br[c]) ? 1 : 0;
+            int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
+            double m = cl == 0 ? m0 : cl == 1 ? m1 : cl == 2 ? m2 : cl == 3 ? m3 : m4;
+            double d = x - m;
+            double dd = d * d;
 #pragma unroll
-            for (int k = 0; k < G; k++) {
-                if (k == cl) { double t = x - mu[k]; ss[k] = fma(t, t, ss[k]); }
+            for (int k = 0; k < GMAX; k++) {
+                if (k == cl) v[k] += dd;
             }
         }
-        warp_sum_vec<G>(ss);
-#pragma unroll
-        for (int k = 0; k < G; k++) sig[k] = ss[k] / acc[k];
+        t = reduce16(v, lane);
+        sig_own = slot(t, kown) / cnt;
     }
 
     double hold = 8.988465674311579e307, hood = 0.0;   // "previous" log-likelihood sentinel (FLMAX/2 in mclust)
     int iter = 0;
-    double A[G], B[G], C[G];
-    bool failed = false;
+    double A = 0.0, B = 0.0, C = 0.0, nh_own = 0.0, lc_own = 0.0;
+    bool failed = false, near_tol = false, capped = false;
     for (;;) {
-        double smin = sig[0];
-#pragma unroll
-        for (int k = 1; k < G; k++) smin = fmin(smin, sig[k]);
-        if (smin <= eps) { failed = true; break; }   // "sigma-squared falls below threshold"
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            nh[k] = -0.5 / sig[k];
-            lc[k] = log(pro[k]) - 0.5 * (PI2LOG + log(sig[k]));
-        }
+        if (__any_sync(FULLMASK, owner && sig_own <= eps)) { failed = true; break; }   // "sigma-squared falls below threshold"
+        nh_own = -0.5 / sig_own;
+        lc_own = log(pro_own) - 0.5 * (PI2LOG + log(sig_own));
         iter++;
-        // ---- E-step fused with the sufficient statistics of the next M-step ----
-#pragma unroll
-        for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
-        double hl = 0.0, pl = 1.0;
-        int since = 0;
-#pragma unroll 2
-        for (int i = lane; i < n; i += 32) {
-            double x = xs[i];
-            double e[G], d[G], q[G], S, tmax;
-            estep_point<G>(x, mu, nh, lc, e, d, q, S, tmax);
-            double rs = __drcp_rn(S);
-#pragma unroll
-            for (int k = 0; k < G; k++) {
-                double z = __dmul_rn(e[k], rs);
-                A[k] += z;
-                B[k] = fma(z, d[k], B[k]);
-                C[k] = fma(z, q[k], C[k]);
-            }
-            // sum_i log S_i as the log of a running product (S in [1, G]); flushed before it can overflow
-            pl *= S;
-            hl += tmax;
-            if (++since == 64) { hl += log(pl); pl = 1.0; since = 0; }
-        }
-        hl += log(pl);
-        {
-            double red[3 * G + 1];
-#pragma unroll
-            for (int k = 0; k < G; k++) { red[k] = A[k]; red[G + k] = B[k]; red[2 * G + k] = C[k]; }
-            red[3 * G] = hl;
-            warp_sum_vec<3 * G + 1>(red);
-#pragma unroll
-            for (int k = 0; k < G; k++) { A[k] = red[k]; B[k] = red[G + k]; C[k] = red[2 * G + k]; }
-            hood = red[3 * G];
-        }
-        st.triples += dn * G;
-        st.point_iters += dn;
+        __syncwarp();
+        if (owner) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
+        __syncwarp();
+        double v[16];
+        estep_dispatch(G, xs, n, lane, pm, tab, v);
+        double t = reduce16(v, lane);
+        A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
+        hood = slot(t, 3 * G);
         double err = fabs(hold - hood) / (1.0 + fabs(hood));
         hold = hood;
-        if (fabs(err - tol) <= 1e-7 * tol) st.tol_near += 1.0;
+        if (fabs(err - tol) <= 1e-7 * tol) near_tol = true;
         if (!(err > tol)) break;
-        if (iter >= EM_ITER_CAP) { st.cap_hits += 1.0; break; }
-        // ---- M-step ----
-        double amin = A[0];
-#pragma unroll
-        for (int k = 1; k < G; k++) amin = fmin(amin, A[k]);
-        if (amin <= rteps) { failed = true; break; }
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            double ra = 1.0 / A[k];
-            double dm = B[k] * ra;
-            mu[k] = mu[k] + dm;
-            sig[k] = fma(-dm, dm, C[k] * ra);
-            pro[k] = A[k] / dn;
-        }
+        if (iter >= EM_ITER_CAP) { capped = true; break; }
+        // ---- M-step (lane k: component k) ----
+        if (__any_sync(FULLMASK, owner && A <= rteps)) { failed = true; break; }
+        double ra = 1.0 / A;
+        double dm = B * ra;
+        mu_own = mu_own + dm;
+        sig_own = fma(-dm, dm, C * ra);
+        pro_own = A / dn;
     }
-    st.em_iters += (double)iter;
-    if (lane == 0) row->iters = iter;
+    if (lane == 0) {
+        // work counters (per warp, shared memory): iterations executed, points x components, points
+        st->em_iters += (double)iter;
+        st->triples += dn * (double)G * (double)iter;
+        st->point_iters += dn * (double)iter;
+        if (near_tol) st->tol_near += 1.0;
+        if (capped) st->cap_hits += 1.0;
+        row->iters = iter;
+    }
     if (failed) return;
 
     // ---- converged: BIC, parameters, labels ----
-    row->loglik = hood;
-    row->bic = 2.0 * hood - (double)(3 * G - 1) * log(dn);
-    bool use_extra = false;
-    double mu2[G], sig2[G];
+    double mean_out = mu_own, sig_out = sig_own;
     if (extra_mstep) {
         // summaryMclustBIC: if sum((pro - colMeans(z))^2) > sqrt(eps) replace $parameters by one more M-step
+        double cm = A / dn;
+        double term = owner ? (pro_own - cm) * (pro_own - cm) : 0.0;
         double dev = 0.0;
-        bool ok = true;
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            double cm = A[k] / dn;
-            dev += (pro[k] - cm) * (pro[k] - cm);
-            if (!(A[k] > 0.0)) ok = false;
-        }
+        for (int k = 0; k < GMAX; k++) dev += __shfl_sync(FULLMASK, term, k);
+        bool ok = !__any_sync(FULLMASK, owner && !(A > 0.0));
         if (dev > rteps && ok) {
-            use_extra = true;
-#pragma unroll
-            for (int k = 0; k < G; k++) {
-                double ra = 1.0 / A[k];
-                double dm = B[k] * ra;
-                mu2[k] = mu[k] + dm;
-                sig2[k] = fma(-dm, dm, C[k] * ra);
-            }
+            double ra = 1.0 / A;
+            double dm = B * ra;
+            mean_out = mu_own + dm;
+            sig_out = fma(-dm, dm, C * ra);
         }
     }
     // MAP labels from the final z (same parameters as the last E-step) and their statistics
-    double lab[3 * G];
-#pragma unroll
-    for (int k = 0; k < 3 * G; k++) lab[k] = 0.0;
-    for (int i = lane; i < n; i += 32) {
-        double x = xs[i];
-        int bk = map_label<G>(x, mu, nh, lc);
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            if (k == bk) { lab[k] += 1.0; lab[G + k] += x; lab[2 * G + k] = fma(x, x, lab[2 * G + k]); }
-        }
+    double v[16];
+    label_dispatch(G, xs, n, lane, pm, tab, v);   // pm still holds the parameters of the last E-step
+    double t = reduce16(v, lane);
+    double cnt = slot(t, kown), sy = slot(t, G + kown), syy = slot(t, 2 * G + kown);
+    if (owner) {
+        row->mean[lane] = mean_out;
+        row->sigsq[lane] = sig_out;
+        row->mu_em[lane] = mu_own;
+        row->nh_em[lane] = nh_own;
+        row->lc_em[lane] = lc_own;
+        row->cnt[lane] = cnt;
+        row->sy[lane] = sy;
+        row->syy[lane] = syy;
     }
-    warp_sum_vec<3 * G>(lab);
     if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            row->mean[k] = use_extra ? mu2[k] : mu[k];
-            row->sigsq[k] = use_extra ? sig2[k] : sig[k];
-            row->mu_em[k] = mu[k];
-            row->nh_em[k] = nh[k];
-            row->lc_em[k] = lc[k];
-            row->cnt[k] = lab[k];
-            row->sy[k] = lab[G + k];
-            row->syy[k] = lab[2 * G + k];
-        }
+        row->loglik = hood;
+        row->bic = 2.0 * hood - (double)(3 * G - 1) * log(dn);
         row->valid = 1;
     }
 }
@@ -428,6 +663,7 @@ struct Tab {   // table(cl): counts of the PRESENT labels in increasing label or
 
 __device__ __forceinline__ int pick_upto(const Row* rows, int k) {   // Mclust(y, "V", G = 1:k): pickBIC, ties -> smaller G
     int best = 0;
+    #pragma unroll 1
     for (int g = 1; g <= k && g <= GMAX; g++) {
         if (!rows[g - 1].valid) continue;
         if (best == 0 || rows[g - 1].bic > rows[best - 1].bic) best = g;
@@ -437,18 +673,21 @@ __device__ __forceinline__ int pick_upto(const Row* rows, int k) {   // Mclust(y
 
 __device__ __forceinline__ void table_of(const Row* rows, int comps, Tab& t) {
     t.nt = 0;
+    #pragma unroll 1
     for (int k = 0; k < comps; k++)
         if (rows[comps - 1].cnt[k] > 0.0) { t.cnt[t.nt] = rows[comps - 1].cnt[k]; t.lab[t.nt] = k; t.nt++; }
 }
 
 __device__ __forceinline__ double tab_min(const Tab& t) {
     double m = t.cnt[0];
+    #pragma unroll 1
     for (int i = 1; i < t.nt; i++) m = fmin(m, t.cnt[i]);
     return m;
 }
 
 __device__ __forceinline__ double r_min_nan(const double* v, int n) {   // R's min(): NaN propagates
     double m = v[0];
+    #pragma unroll 1
     for (int i = 0; i < n; i++) { if (isnan(v[i])) return nan(""); if (v[i] < m) m = v[i]; }
     return m;
 }
@@ -456,12 +695,14 @@ __device__ __forceinline__ double r_min_nan(const double* v, int n) {   // R's m
 // diagnostics of a >= 2 component model: variance ratio and the min/max-variance component indices
 __device__ __forceinline__ void var_diag(const Row& mc, int comps, int& maxcl, int& mincl, double& vardiff, double& sdmax) {
     maxcl = 0; mincl = 0;
+    #pragma unroll 1
     for (int k = 1; k < comps; k++) {
         if (mc.sigsq[k] > mc.sigsq[maxcl]) maxcl = k;   // which.max / which.min: first extremum
         if (mc.sigsq[k] < mc.sigsq[mincl]) mincl = k;
     }
     vardiff = mc.sigsq[maxcl] / mc.sigsq[mincl];
     sdmax = 0.0;
+    #pragma unroll 1
     for (int k = 0; k < comps; k++) sdmax = fmax(sdmax, sqrt(mc.sigsq[k]));
 }
 
@@ -489,17 +730,20 @@ __device__ __noinline__ int restricted_select(const Row* rows, int n, const DevC
             int maxcl, mincl;
             double vardiff, sdmax;
             var_diag(*mc, comps, maxcl, mincl, vardiff, sdmax);        // :79-82
+            #pragma unroll 1
             for (int j = 0; j < nmd; j++) meandiff[j] = (mc->mean[j + 1] - mc->mean[j]) / sdmax;   // :77
             double nmin = (mincl < tb.nt) ? tb.cnt[mincl] : NaN;       // :83  table(cl)[min.cl] is positional
             double mincat = tab_min(tb);                               // :84
             int tries = 0;
             double nmax = (maxcl < tb.nt) ? tb.cnt[maxcl] : NaN;       // :86
             double balance = 2.0 * sqrt(nmin * nmax / ((nmin + nmax) * (nmin + nmax)));   // :87
+            #pragma unroll 1
             for (int j = 0; j < nmd; j++) meandiff[j] *= balance;      // :88
             if (isnan(vardiff)) vardiff = 1.0;                         // :91-110
             if (isnan(nmin)) nmin = INFINITY;
             {
                 bool anyna = false;
+                #pragma unroll 1
                 for (int j = 0; j < nmd; j++) anyna |= isnan(meandiff[j]);
                 if (nmd == 0 || anyna) { meandiff[0] = INFINITY; nmd = 1; }
             }
@@ -516,12 +760,14 @@ __device__ __noinline__ int restricted_select(const Row* rows, int n, const DevC
                     // :129 by(y, cl, mean): empirical means of the present labels
                     var_diag(*mc, comps, maxcl, mincl, vardiff, sdmax);
                     nmd = tb.nt - 1;
+                    #pragma unroll 1
                     for (int j = 0; j < nmd; j++) {
                         double m1 = mc->sy[tb.lab[j + 1]] / tb.cnt[j + 1];
                         double m0 = mc->sy[tb.lab[j]] / tb.cnt[j];
                         meandiff[j] = (m1 - m0) / sdmax;               // :130
                     }
                     balance = 2.0 * sqrt(nmin * nmax / ((nmin + nmax) * (nmin + nmax)));   // :131 (stale nmin / nmax)
+                    #pragma unroll 1
                     for (int j = 0; j < nmd; j++) meandiff[j] *= balance;
                     nmin = (mincl < tb.nt) ? tb.cnt[mincl] : NaN;      // :138
                 } else {
@@ -531,6 +777,7 @@ __device__ __noinline__ int restricted_select(const Row* rows, int n, const DevC
                 if (isnan(nmin)) { nmin = INFINITY; err = 1; }
                 {
                     bool anyna = false;
+                    #pragma unroll 1
                     for (int j = 0; j < nmd; j++) anyna |= isnan(meandiff[j]);
                     if (nmd == 0 || anyna) { meandiff[0] = INFINITY; nmd = 1; err = 1; }
                 }
@@ -565,6 +812,7 @@ __device__ __noinline__ int restricted_select(const Row* rows, int n, const DevC
     // :230-237 every cluster smaller than min.size -> drop one component
     {
         double mx = 0.0;
+        #pragma unroll 1
         for (int i = 0; i < tb.nt; i++) mx = fmax(mx, tb.cnt[i]);
         if (comps > 1 && mx < (double)cfg.min_size) {
             comps = pick_upto(rows, comps - 1);
@@ -575,7 +823,9 @@ __device__ __noinline__ int restricted_select(const Row* rows, int n, const DevC
 
 // order(mc$parameters$mean), stable (R/mclust.restricted.R:243)
 __device__ __forceinline__ void mean_order(const Row& mc, int comps, int* ord) {
+    #pragma unroll 1
     for (int k = 0; k < comps; k++) ord[k] = k;
+    #pragma unroll 1
     for (int i = 1; i < comps; i++) {
         int o = ord[i];
         int j = i - 1;
@@ -591,8 +841,10 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
     int ord[GMAX];
     mean_order(mc, comps, ord);
     double nk[GMAX], sy[GMAX], syy[GMAX];
+    #pragma unroll 1
     for (int k = 0; k < GMAX; k++) { nk[k] = 0.0; sy[k] = 0.0; syy[k] = 0.0; }
     int r = 0;
+    #pragma unroll 1
     for (int l = 0; l < comps; l++) {
         // cl2[cl == l] <- as.numeric(names(mean[order(mean)])[l])  (order(), not rank(): quirk viii)
         int nl = (comps > 1) ? ord[l] : l;
@@ -601,7 +853,9 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
     }
     const double alpha = cfg.alpha, m0 = cfg.m0, s0 = cfg.s0, a0 = cfg.a0, b0 = cfg.b0;
     double logpost = 0.0, J = 0.0;
+    #pragma unroll 1
     for (int k = 0; k < r; k++) J += nk[k];
+    #pragma unroll 1
     for (int k = 0; k < r; k++) {
         double sk = s0 + nk[k];
         double mk = (s0 * m0 + sy[k]) / sk;
@@ -619,25 +873,27 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
 // ---------------------------------------------------------------------------------------------
 // The whole fit-set on a sorted slab.  Returns the selected number of components (0 = failed).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* rows, const DevCfg& cfg, WarpStats& st) {
+__device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* rows, const DevCfg& cfg, WarpStats* st,
+                                       double* pm, const double* tab) {
     fit_row1(xs, n, lane, &rows[0]);
-    fit_row<2>(xs, n, lane, &rows[1], st, cfg.extra_mstep);
-    fit_row<3>(xs, n, lane, &rows[2], st, cfg.extra_mstep);
-    fit_row<4>(xs, n, lane, &rows[3], st, cfg.extra_mstep);
-    fit_row<5>(xs, n, lane, &rows[4], st, cfg.extra_mstep);
+    for (int G = 2; G <= GMAX; G++) fit_row(G, xs, n, lane, &rows[G - 1], st, pm, tab, cfg.extra_mstep);
     __syncwarp();
-    st.fit_sets += 1.0;
     // near-tie diagnostic: two best BICs within 1e-9 relative
+    bool bic_near = false;
     {
         double b1 = -INFINITY, b2 = -INFINITY;
         for (int g = 0; g < GMAX; g++) if (rows[g].valid) {
             double b = rows[g].bic;
             if (b > b1) { b2 = b1; b1 = b; } else if (b > b2) b2 = b;
         }
-        if (b2 > -INFINITY && fabs(b1 - b2) <= 1e-9 * fabs(b1)) st.bic_near += 1.0;
+        if (b2 > -INFINITY && fabs(b1 - b2) <= 1e-9 * fabs(b1)) bic_near = true;
     }
     int comps = restricted_select(rows, n, cfg);
-    if (comps == 0) st.failed_sets += 1.0;
+    if (lane == 0) {
+        st->fit_sets += 1.0;
+        if (bic_near) st->bic_near += 1.0;
+        if (comps == 0) st->failed_sets += 1.0;
+    }
     return comps;
 }
 

@@ -138,22 +138,35 @@ __device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int
 }
 
 template <int G>
-__device__ __forceinline__ int label_of(const Row& r, double x) {
-    double mu[G], nh[G], lc[G];
+__device__ __noinline__ int label_of(const Row& r, double x) {
+    ParamsReg<G> p;
+    p.tab = EXP_TABLE_GLOBAL;
 #pragma unroll
-    for (int k = 0; k < G; k++) { mu[k] = r.mu_em[k]; nh[k] = r.nh_em[k]; lc[k] = r.lc_em[k]; }
-    return map_label<G>(x, mu, nh, lc);
+    for (int k = 0; k < G; k++) { p.mu[k] = r.mu_em[k]; p.nh[k] = r.nh_em[k]; p.lc[k] = r.lc_em[k]; }
+    return map_label<G>(x, p);
 }
 
-constexpr int FIT_MAX_WARPS = 16;
+#ifndef SCDD_FIT_WARPS
+#define SCDD_FIT_WARPS 16
+#endif
+constexpr int FIT_MAX_WARPS = SCDD_FIT_WARPS;
+__host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
+    return (size_t)np * sizeof(double) + 4 * GMAX * sizeof(double) + GMAX * sizeof(Row) + sizeof(WarpStats);
+}
 
 __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = (size_t)a.np_max * sizeof(double) + GMAX * sizeof(Row);
-    double* xs = reinterpret_cast<double*>(smem_raw + warp * per_warp);
-    Row* rows = reinterpret_cast<Row*>(xs + a.np_max);
-    WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t per_warp = fit_smem_per_warp(a.np_max);
+    double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/32), shared by the CTA
+    if (threadIdx.x < 32) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    __syncthreads();
+    double* xs = reinterpret_cast<double*>(smem_raw + 256 + warp * per_warp);
+    double* pm = xs + a.np_max;                       // {mu, nh, lc, pad} x GMAX, 16-byte aligned
+    Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
+    WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
+    if (lane == 0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    __syncwarp();
     const long long total = (long long)a.ngenes * a.nb * a.sets;
     const double NaN = nan("");
 
@@ -195,10 +208,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
         if (n < 1 || xs[0] == xs[n - 1]) {
             // all values identical: the reference jitters with runif() (R/mclust.restricted.R:48-50),
             // which consumes RNG state mid-stream; reported, never silently fitted
-            st.const_sets += 1.0;
-            st.failed_sets += 1.0;
+            if (lane == 0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
         } else {
-            comps = fit_set(xs, n, lane, rows, a.cfg, st);
+            comps = fit_set(xs, n, lane, rows, a.cfg, st, pm, tab);
             if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
         }
         if (lane == 0) a.jp[item] = jp;
@@ -244,9 +256,10 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     }
 
     // ---- flush the work counters ----
-    double v[9] = {st.triples, st.point_iters, st.em_iters, st.cap_hits, st.tol_near,
-                   st.bic_near, st.const_sets, st.failed_sets, st.fit_sets};
+    __syncwarp();
     if (lane == 0) {
+        double v[9] = {st->triples, st->point_iters, st->em_iters, st->cap_hits, st->tol_near,
+                       st->bic_near, st->const_sets, st->failed_sets, st->fit_sets};
 #pragma unroll
         for (int k = 0; k < 9; k++) if (v[k] != 0.0) atomicAdd(&a.stats[k], v[k]);
     }

@@ -251,15 +251,15 @@ struct Pipeline {
     void launch_fit(cudaStream_t s, FitArgs a, int nmax_points) {
         int np = 2;
         while (np < nmax_points) np <<= 1;
-        const size_t per_warp = (size_t)np * sizeof(double) + GMAX * sizeof(Row);
-        const size_t smem_cap = 227 * 1024;
+        const size_t per_warp = fit_smem_per_warp(np);
+        const size_t smem_cap = 227 * 1024 - 256;   // 256 B: the CTA's 2^(j/32) table
         int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
         if (warps < 1)
             throw ScddError{SCDD_ERR_TOO_LARGE, "a fit-set of " + std::to_string(nmax_points) +
                             " points does not fit the shared-memory slab of the warp-per-fit kernel"};
         const long long total = (long long)a.ngenes * a.nb * a.sets;
         if (total == 0) return;
-        const size_t smem = per_warp * warps;
+        const size_t smem = per_warp * warps + 256;
         CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long want = (total + warps - 1) / warps;
         int grid = (int)std::min<long long>(n_sm, want);
@@ -840,7 +840,8 @@ int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out) {
 }
 
 int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
-    for (int i = 0; i < n; i++) out[i] = exp_neg(x[i]);
+    static const double tab[32] = SCDD_EXP_TABLE_INIT;
+    for (int i = 0; i < n; i++) out[i] = exp_neg(x[i], tab);   // the variant the kernels are built with
     return SCDD_OK;
 }
 
