@@ -1,0 +1,117 @@
+/*
+ * scdd_glue.c -- .Call glue between the reference's R code and libscdd_b200.so.
+ *
+ * NOT COMPILED IN THE BUILD IMAGE (no R headers there); built by `R CMD INSTALL` where R exists:
+ *   PKG_CPPFLAGS = -I<repo>/include     PKG_LIBS = -L<repo>/scdd_b200 -lscdd_b200
+ * Pure marshalling: R vectors in, R vectors out; errors are raised with Rf_error() only AFTER the library
+ * call has returned (never a longjmp through C++/CUDA frames).  Must be called from the master R process,
+ * not from inside bplapply workers (CUDA contexts do not survive fork()).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "scdd_b200.h"
+
+static scdd_cfg cfg_from(SEXP prior, SEXP min_size) {
+    /* prior = c(alpha, mu0, s0, a0, b0)  (R/scDD.R:245-249) */
+    scdd_cfg c;
+    scdd_default_cfg(&c);
+    const double *p = REAL(prior);
+    c.alpha = p[0]; c.m0 = p[1]; c.s0 = p[2]; c.a0 = p[3]; c.b0 = p[4];
+    c.min_size = asInteger(min_size);
+    return c;
+}
+
+/* gene_off is passed from R as a double vector (R has no int64): converted here */
+static int64_t *offsets(SEXP off, int *ngenes) {
+    int n = LENGTH(off);
+    int64_t *o = (int64_t *)R_alloc(n, sizeof(int64_t));
+    for (int i = 0; i < n; i++) o[i] = (int64_t)REAL(off)[i];
+    *ngenes = n - 1;
+    return o;
+}
+
+/* genefit over all genes: replaces the bplapply at R/scDD.R:343 / :393 */
+SEXP C_scdd_fit_observed(SEXP logy, SEXP off, SEXP cond01, SEXP prior, SEXP min_size, SEXP want_bf) {
+    int ng;
+    int64_t *o = offsets(off, &ng);
+    scdd_cfg cfg = cfg_from(prior, min_size);
+    R_xlen_t nnz = XLENGTH(logy);
+    SEXP fits = PROTECT(allocVector(RAWSXP, (R_xlen_t)3 * ng * sizeof(scdd_fit)));
+    SEXP cls_oa = PROTECT(allocVector(INTSXP, nnz));
+    SEXP cls_c = PROTECT(allocVector(INTSXP, nnz));
+    SEXP bf = PROTECT(allocVector(REALSXP, ng));
+    SEXP den = PROTECT(allocVector(REALSXP, ng));
+    int wb = asLogical(want_bf);
+    scdd_stats st;
+    int rc = scdd_fit_observed(REAL(logy), o, INTEGER(cond01), ng, &cfg, (scdd_fit *)RAW(fits),
+                               INTEGER(cls_oa), INTEGER(cls_c), wb ? REAL(bf) : NULL, wb ? REAL(den) : NULL, &st);
+    if (rc != SCDD_OK && rc != SCDD_ERR_FIT_FAILED) { UNPROTECT(5); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    /* unpack scdd_fit into numeric matrices so the R side can rebuild the mclustRestricted lists */
+    SEXP G = PROTECT(allocVector(INTSXP, 3 * ng)), bic = PROTECT(allocVector(REALSXP, 3 * ng));
+    SEXP ll = PROTECT(allocVector(REALSXP, 3 * ng)), n = PROTECT(allocVector(INTSXP, 3 * ng));
+    SEXP mean = PROTECT(allocMatrix(REALSXP, SCDD_GMAX, 3 * ng)), var = PROTECT(allocMatrix(REALSXP, SCDD_GMAX, 3 * ng));
+    const scdd_fit *f = (const scdd_fit *)RAW(fits);
+    for (int i = 0; i < 3 * ng; i++) {
+        INTEGER(G)[i] = f[i].G; INTEGER(n)[i] = f[i].n; REAL(bic)[i] = f[i].bic; REAL(ll)[i] = f[i].loglik;
+        memcpy(REAL(mean) + (size_t)SCDD_GMAX * i, f[i].mean, sizeof(double) * SCDD_GMAX);
+        memcpy(REAL(var) + (size_t)SCDD_GMAX * i, f[i].var, sizeof(double) * SCDD_GMAX);
+    }
+    const char *nm[] = {"G", "n", "bic", "loglik", "mean", "var", "class.oa", "class.c", "bf", "den", ""};
+    SEXP out = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(out, 0, G); SET_VECTOR_ELT(out, 1, n); SET_VECTOR_ELT(out, 2, bic); SET_VECTOR_ELT(out, 3, ll);
+    SET_VECTOR_ELT(out, 4, mean); SET_VECTOR_ELT(out, 5, var); SET_VECTOR_ELT(out, 6, cls_oa);
+    SET_VECTOR_ELT(out, 7, cls_c); SET_VECTOR_ELT(out, 8, bf); SET_VECTOR_ELT(out, 9, den);
+    UNPROTECT(12);
+    return out;
+}
+
+/* permMclustGene / permMclust / permMclustCov over all genes: replaces R/scDD.R:420-465.
+ * perm_idx: integer vector from R's own sample() calls (or NULL); seed6: integer matrix 6 x ngenes of
+ * .Random.seed[2:7] per gene (or NULL); cdr: numeric (adjust.perms) or NULL. */
+SEXP C_scdd_perm_bf(SEXP logy, SEXP off, SEXP cond01, SEXP B, SEXP perm_idx, SEXP seed6, SEXP cdr,
+                    SEXP prior, SEXP min_size) {
+    int ng;
+    int64_t *o = offsets(off, &ng);
+    scdd_cfg cfg = cfg_from(prior, min_size);
+    int b = asInteger(B);
+    SEXP out = PROTECT(allocMatrix(REALSXP, b, ng));   /* column g = bf.perm[[g]] */
+    scdd_stats st;
+    int rc = scdd_perm_bf(REAL(logy), o, INTEGER(cond01), ng, b,
+                          isNull(perm_idx) ? NULL : INTEGER(perm_idx),
+                          isNull(seed6) ? NULL : (const uint32_t *)INTEGER(seed6),
+                          isNull(cdr) ? NULL : REAL(cdr), &cfg, REAL(out), NULL, &st);
+    if (rc != SCDD_OK && rc != SCDD_ERR_FIT_FAILED) { UNPROTECT(1); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    UNPROTECT(1);
+    return out;
+}
+
+/* testKS::onegene over all genes: replaces the bplapply at R/Test_KS.R:67 */
+SEXP C_scdd_ks(SEXP vals, SEXP off, SEXP cond01) {
+    int ng;
+    int64_t *o = offsets(off, &ng);
+    SEXP D = PROTECT(allocVector(REALSXP, ng)), p = PROTECT(allocVector(REALSXP, ng));
+    int rc = scdd_ks(REAL(vals), o, INTEGER(cond01), ng, 0, REAL(D), REAL(p), NULL);
+    if (rc != SCDD_OK) { UNPROTECT(2); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    const char *nm[] = {"D", "p", ""};
+    SEXP out = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(out, 0, D); SET_VECTOR_ELT(out, 1, p);
+    UNPROTECT(3);
+    return out;
+}
+
+SEXP C_scdd_device_count(void) { return ScalarInteger(scdd_device_count()); }
+
+static const R_CallMethodDef calls[] = {
+    {"C_scdd_fit_observed", (DL_FUNC)&C_scdd_fit_observed, 6},
+    {"C_scdd_perm_bf", (DL_FUNC)&C_scdd_perm_bf, 9},
+    {"C_scdd_ks", (DL_FUNC)&C_scdd_ks, 3},
+    {"C_scdd_device_count", (DL_FUNC)&C_scdd_device_count, 0},
+    {NULL, NULL, 0}};
+
+void R_init_scDD(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, calls, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

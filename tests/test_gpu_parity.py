@@ -181,3 +181,40 @@ def test_synthetic_bimodal_and_small_genes():
     assert np.array_equal(cls_oa, ocls_oa) and np.array_equal(cls_c, ocls_c)
     np.testing.assert_allclose(bf, obf, rtol=RTOL)
     np.testing.assert_allclose(den, oden, rtol=RTOL)
+
+
+def test_scdd_api_end_to_end(golden_dir):
+    """host mirror of scDD(): permutations = 20 on scDatExSim (config 2) and the KS path (config 1)"""
+    from scdd_b200 import api
+    X, cond = _load(golden_dir, "scDatExSim.npz")
+    d = np.load(os.path.join(golden_dir, "scDatExSim.npz"), allow_pickle=True)
+    pri = dict(alpha=0.01, mu0=0, s0=0.01, a0=0.01, b0=0.01)
+    sce = api.SingleCellExperiment({"normcounts": X}, {"condition": cond}, rownames=[str(g) for g in d["genes"]])
+    out = api.scDD(sce, prior_param=pri, permutations=20, testZeroes=False, param={"RNGseed": 7}, verbose=False)
+    G = api.results(out, "Genes")
+    assert list(G.keys())[:7] == ["gene", "DDcategory", "Clusters.combined", "Clusters.c1", "Clusters.c2",
+                                  "nonzero.pvalue", "nonzero.pvalue.adj"]
+    # same permutations drawn on the host give the same p-values
+    sce2 = api.SingleCellExperiment({"normcounts": X}, {"condition": cond})
+    out2 = api.scDD(sce2, prior_param=pri, permutations=20, testZeroes=False, param={"RNGseed": 7},
+                    perm_source="host", verbose=False)
+    assert np.array_equal(G["nonzero.pvalue"], api.results(out2, "Genes")["nonzero.pvalue"])
+    # oracle p-values from the same streams
+    logy, c01, off = hp.gene_csr(X, cond)
+    ref = po.perm_batch(logy, c01, off, 20, seed6=hp.gene_seeds(7, 30), cfg=po.make_cfg(**PRIORS))
+    _, _, _, obf, _ = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    assert np.array_equal(G["nonzero.pvalue"], (ref > obf[:, None]).sum(1) / 20.0)
+    Z = api.results(out, "Zhat.combined")
+    assert Z.shape == X.shape and np.array_equal(Z == 0, X == 0)
+    assert api.results(out, "Zhat.c1").shape == (30, 100) and api.results(out, "Zhat.c2").shape == (30, 100)
+    # DD genes of the simulated example (rows DE/DP/DM/DB) should mostly get small p, EE/EP large
+    p = G["nonzero.pvalue"]
+    assert np.median(p[:20]) < np.median(p[20:])
+    # permutations = 0 -> KS path (R/scDD.R:359-368)
+    sce3 = api.SingleCellExperiment({"normcounts": X}, {"condition": cond})
+    out3 = api.scDD(sce3, prior_param=pri, permutations=0, testZeroes=False, verbose=False)
+    vals, ck, offk = hp.gene_csr(X, cond, log=False)
+    _, op = po.ks_batch(vals, ck, offk)
+    assert np.array_equal(api.results(out3, "Genes")["nonzero.pvalue"], op)
+    ks = api.testKS(X, cond, inclZero=False, numDE=20, DEIndex=np.arange(1, 21))
+    assert set(ks.keys()) == {"genes", "p", "p.unadj", "power", "fdr"} and 0 <= ks["power"] <= 1
