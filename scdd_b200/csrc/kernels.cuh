@@ -104,6 +104,139 @@ __global__ void permgen_kernel(const int64_t* __restrict__ off, int ngenes, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// permutations, warp per gene.  R's stream is serial per gene, but only the Fisher-Yates consumption has
+// to be: the MRG32k3a outputs themselves are produced 32 at a time.  Decimating a linear recurrence of
+// order 3 by 32 gives another order-3 recurrence, z[j+3] = b2 z[j+2] + b1 z[j+1] + b0 z[j] (mod m), whose
+// coefficients are those of the characteristic polynomial of A^32 (computed on the host); lane l produces
+// outputs l, l+32, l+64, ... of the stream.  Lane 0 then consumes the 16-bit chunks exactly as
+// R_unif_index / do_sample do, with the Fisher-Yates array in shared memory, and the finished permutation
+// is written out coalesced by the whole warp.  Bit-identical to permgen_kernel and to R.
+// ------------------------------------------------------------------------------------------------
+struct MrgDecim {
+    uint32_t b1[3], b2[3];   // {b0, b1, b2} for the two components (moduli MRG_M1, MRG_M2)
+};
+
+constexpr int PG_BLOCK = 256;   // uniforms generated per refill (8 per lane)
+
+__device__ __forceinline__ uint32_t mrg_rec3(const uint32_t* c, uint32_t z0, uint32_t z1, uint32_t z2, uint64_t m) {
+    uint64_t s = ((uint64_t)c[0] * z0) % m + ((uint64_t)c[1] * z1) % m + ((uint64_t)c[2] * z2) % m;
+    return (uint32_t)(s % m);
+}
+
+__host__ __device__ constexpr size_t permgen_smem_per_warp(int nmax, int idx_bytes) {
+    return ((size_t)nmax * idx_bytes + 15) / 16 * 16 + 2 * (PG_BLOCK + 3) * sizeof(uint32_t) + 8 +
+           PG_BLOCK * sizeof(uint16_t);
+}
+
+template <class IdxT>
+__global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes, uint32_t* __restrict__ seeds,
+                                    IdxT* __restrict__ perm_out, int nb, MrgDecim dc, int nmax) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char* base = smem_raw + warp * permgen_smem_per_warp(nmax, (int)sizeof(IdxT));
+    IdxT* arr = reinterpret_cast<IdxT*>(base);
+    uint32_t* Xr = reinterpret_cast<uint32_t*>(base + ((size_t)nmax * sizeof(IdxT) + 15) / 16 * 16);
+    uint32_t* Yr = Xr + (PG_BLOCK + 3) + 1;
+    uint16_t* cand = reinterpret_cast<uint16_t*>(Yr + (PG_BLOCK + 3) + 1);
+
+    for (int g = blockIdx.x * wpb + warp; g < ngenes; g += gridDim.x * wpb) {
+        const int64_t o = off[g];
+        const uint32_t n = (uint32_t)(off[g + 1] - o);
+        // ---- stream start: raw values X_0..X_98 / Y_0..Y_98 by plain stepping, then the lane windows ----
+        __syncwarp();
+        if (lane == 0) {
+            Lecuyer st;
+            for (int j = 0; j < 6; j++) st.s[j] = seeds[(size_t)g * 6 + j];
+            Xr[0] = st.s[0]; Xr[1] = st.s[1]; Xr[2] = st.s[2];
+            Yr[0] = st.s[3]; Yr[1] = st.s[4]; Yr[2] = st.s[5];
+            for (int t = 0; t < 96; t++) {
+                lecuyer_unif(st);
+                Xr[3 + t] = st.s[2];
+                Yr[3 + t] = st.s[5];
+            }
+        }
+        __syncwarp();
+        uint32_t x0 = Xr[3 + lane], x1 = Xr[35 + lane], x2 = Xr[67 + lane];
+        uint32_t y0 = Yr[3 + lane], y1 = Yr[35 + lane], y2 = Yr[67 + lane];
+        __syncwarp();
+        int used = PG_BLOCK;          // forces a refill first
+        bool first_block = true;
+        IdxT* gout = perm_out + (size_t)o * nb;
+        for (int b = 0; b < nb; b++) {
+            for (uint32_t i = lane; i < n; i += 32) arr[i] = (IdxT)i;
+            __syncwarp();
+            uint32_t i = 0, m = n;
+            int bits = index_bits(m);
+            int need = bits / 16 + 1;
+            uint64_t vacc = 0;
+            while (i < n) {
+                if (used == PG_BLOCK) {
+                    // ---- refill: 8 outputs per lane ----
+                    if (!first_block && lane < 3) { Xr[lane] = Xr[PG_BLOCK + lane]; Yr[lane] = Yr[PG_BLOCK + lane]; }
+                    first_block = false;
+                    __syncwarp();
+#pragma unroll 1
+                    for (int j = 0; j < PG_BLOCK / 32; j++) {
+                        const int t = 32 * j + lane;
+                        Xr[3 + t] = x0; Yr[3 + t] = y0;
+                        int64_t p1 = (int64_t)x0, p2 = (int64_t)y0;
+                        int64_t d = (p1 > p2) ? (p1 - p2) : (p1 - p2 + MRG_M1);
+                        double u = r_fixup((double)d * 2.328306549295727688e-10);
+                        cand[t] = (uint16_t)(int)floor(u * 65536.0);
+                        uint32_t xn = mrg_rec3(dc.b1, x0, x1, x2, (uint64_t)MRG_M1);
+                        uint32_t yn = mrg_rec3(dc.b2, y0, y1, y2, (uint64_t)MRG_M2);
+                        x0 = x1; x1 = x2; x2 = xn;
+                        y0 = y1; y1 = y2; y2 = yn;
+                    }
+                    used = 0;
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
+                    const uint64_t one = 1;
+                    uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                    while (i < n && used < PG_BLOCK) {
+                        vacc = 65536ULL * vacc + (uint64_t)cand[used++];
+                        if (--need == 0) {
+                            uint64_t v = vacc & mask;
+                            if (v < (uint64_t)m) {
+                                // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the
+                                // active range receives y[i]: the array ends up holding the permutation reversed.
+                                const IdxT pick = arr[v];
+                                --m;
+                                arr[v] = arr[m];
+                                arr[m] = pick;
+                                i++;
+                                if ((m & (m - 1)) == 0) {   // ceil(log2 m) changes only at powers of two
+                                    bits = index_bits(m);
+                                    mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                }
+                            }
+                            vacc = 0;
+                            need = bits / 16 + 1;
+                        }
+                    }
+                }
+                i = __shfl_sync(FULLMASK, i, 0);
+                used = __shfl_sync(FULLMASK, used, 0);
+                __syncwarp();
+            }
+            for (uint32_t k = lane; k < n; k += 32) gout[(size_t)b * n + k] = arr[n - 1 - k];
+            __syncwarp();
+        }
+        // ---- state after exactly the consumed outputs: (X_T, X_T+1, X_T+2), T = block start + used ----
+        if (lane == 0) {
+            // X_{Tb + used + k} for k = 0..2 live in Xr[used + k] (Xr[0..2] is the state at the block start)
+            for (int k = 0; k < 3; k++) {
+                seeds[(size_t)g * 6 + k] = Xr[used + k];
+                seeds[(size_t)g * 6 + 3 + k] = Yr[used + k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mixture fits
 // ------------------------------------------------------------------------------------------------
 enum PermKind { PERM_NONE = 0, PERM_I32_1BASED = 1, PERM_U16 = 2, PERM_U32 = 3 };

@@ -115,6 +115,34 @@ void apply_jump(const Mat3& A1, const Mat3& A2, const uint32_t* in, uint32_t* ou
     std::memcpy(out, t, sizeof(t));
 }
 
+// coefficients {b0, b1, b2} of z[j+3] = b2 z[j+2] + b1 z[j+1] + b0 z[j] (mod m) obeyed by every 2^e-decimated
+// subsequence: the characteristic polynomial of M = A^(2^e), lambda^3 = tr(M) lambda^2 - minors(M) lambda + det(M)
+void charpoly3(const Mat3& M, uint64_t m, uint32_t* b) {
+    auto mulm = [&](uint64_t x, uint64_t y) { return (uint64_t)((u128)x * y % m); };
+    auto subm = [&](uint64_t x, uint64_t y) { return (x + m - y % m) % m; };
+    const auto& a = M.a;
+    uint64_t tr = (a[0][0] + a[1][1] + a[2][2]) % m;
+    uint64_t minors = (subm(mulm(a[0][0], a[1][1]), mulm(a[0][1], a[1][0])) +
+                       subm(mulm(a[0][0], a[2][2]), mulm(a[0][2], a[2][0])) +
+                       subm(mulm(a[1][1], a[2][2]), mulm(a[1][2], a[2][1]))) % m;
+    uint64_t det = 0;
+    det = (det + mulm(a[0][0], subm(mulm(a[1][1], a[2][2]), mulm(a[1][2], a[2][1])))) % m;
+    det = subm(det, mulm(a[0][1], subm(mulm(a[1][0], a[2][2]), mulm(a[1][2], a[2][0]))));
+    det = (det + mulm(a[0][2], subm(mulm(a[1][0], a[2][1]), mulm(a[1][1], a[2][0])))) % m;
+    b[0] = (uint32_t)det;
+    b[1] = (uint32_t)((m - minors) % m);
+    b[2] = (uint32_t)tr;
+}
+
+MrgDecim decimation_by_32() {
+    Mat3 A1, A2;
+    jump_matrices(5, A1, A2);   // A^(2^5) = A^32
+    MrgDecim d;
+    charpoly3(A1, (uint64_t)MRG_M1, d.b1);
+    charpoly3(A2, (uint64_t)MRG_M2, d.b2);
+    return d;
+}
+
 struct MersenneTwister {   // R's default kind
     uint32_t mt[624];
     int mti;
@@ -312,15 +340,35 @@ struct Pipeline {
     // permgen + fit + combine for nb permutations; bf_out[g * ld + col0 + b]
     void run_chunk_device_perms(cudaStream_t s, int nb, double* bf_out, long long ld, int col0) {
         if (ngenes == 0 || nb == 0) return;
-        const int tpb = 64;
         Timed tr;
         if (time_kernels) tr = tick_begin(1, s);
-        if (wide_idx)
-            permgen_kernel<uint32_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
-                (uint32_t*)d_scratch.p, (uint32_t*)d_perm.p, nb);
-        else
-            permgen_kernel<uint16_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
-                (uint16_t*)d_scratch.p, (uint16_t*)d_perm.p, nb);
+        {
+            static const MrgDecim dc = decimation_by_32();
+            const int ib = (int)idx_bytes();
+            const size_t per_warp = permgen_smem_per_warp(max_n, ib);
+            const size_t cap = 200 * 1024;
+            if (per_warp <= cap) {
+                int wpb = (int)std::max<size_t>(1, std::min<size_t>(4, cap / per_warp));
+                size_t smem = per_warp * wpb;
+                int grid = std::min((ngenes + wpb - 1) / wpb, n_sm * std::max(1, std::min(16, (int)(cap / smem))));
+                if (wide_idx) {
+                    CK(cudaFuncSetAttribute(permgen_warp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    permgen_warp_kernel<uint32_t><<<grid, wpb * 32, smem, s>>>(d_off.p, ngenes, d_seeds.p, (uint32_t*)d_perm.p, nb, dc, max_n);
+                } else {
+                    CK(cudaFuncSetAttribute(permgen_warp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    permgen_warp_kernel<uint16_t><<<grid, wpb * 32, smem, s>>>(d_off.p, ngenes, d_seeds.p, (uint16_t*)d_perm.p, nb, dc, max_n);
+                }
+            } else {
+                // genes too long for the shared-memory Fisher-Yates array: thread-per-gene kernel, global scratch
+                const int tpb = 64;
+                if (wide_idx)
+                    permgen_kernel<uint32_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
+                        (uint32_t*)d_scratch.p, (uint32_t*)d_perm.p, nb);
+                else
+                    permgen_kernel<uint16_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
+                        (uint16_t*)d_scratch.p, (uint16_t*)d_perm.p, nb);
+            }
+        }
         CK(cudaGetLastError());
         if (time_kernels) tick_end(tr, s);
         FitArgs a = base_args();
