@@ -352,6 +352,34 @@ __device__ __forceinline__ double reduce16(double (&v)[16], int lane) {
 }
 __device__ __forceinline__ double slot(double t, int e) { return __shfl_sync(FULLMASK, t, 2 * e); }
 
+// A fit-set is executed by a "team": one warp (TW = 1; the vector lives in the warp's shared-memory slab) or a
+// whole CTA of TW warps (large vectors; shared or global memory).  Every thread of a team follows the same
+// control flow on identical reduced values, so team-wide barriers inside the fit are legal.
+template <int TW>
+struct Team {
+    static constexpr int NT = 32 * TW;
+    __device__ __forceinline__ static int tid(int lane) { return TW == 1 ? lane : (int)threadIdx.x; }
+    __device__ __forceinline__ static void sync() {
+        if (TW == 1) __syncwarp(); else __syncthreads();
+    }
+    __device__ __forceinline__ static bool lead() { return TW == 1 || (threadIdx.x >> 5) == 0; }
+    // all-reduce of 16 slots: afterwards lane L of EVERY warp holds the team total of slot (L >> 1)
+    __device__ __forceinline__ static double reduce(double (&v)[16], int lane, double* red) {
+        double t = reduce16(v, lane);
+        if (TW > 1) {
+            const int w = threadIdx.x >> 5;
+            __syncthreads();
+            if ((lane & 1) == 0) red[w * 16 + (lane >> 1)] = t;
+            __syncthreads();
+            double s = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < TW; k++) s += red[k * 16 + (lane >> 1)];
+            t = s;
+        }
+        return t;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // E-step over the warp's points fused with the sufficient statistics of the next M-step.
 // Component k's parameters live in lane k ("owner lane"); they are broadcast into registers here.
@@ -401,30 +429,31 @@ __device__ __forceinline__ auto load_params(const double* pm, const double* tab)
 #endif
 }
 
-template <int G, int U>
+template <int G, int U, int TW>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            const double* tab, double (&v)[16]) {
+    constexpr int NT = Team<TW>::NT;
     const auto prm = load_params<G>(pm, tab);
     double A[G], B[G], C[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
     double hl = 0.0;
-    constexpr int CHUNK = 256 * 32;   // the running product is flushed every 256 points per lane (5^256 < DBL_MAX)
+    constexpr int CHUNK = 256 * NT;   // the running product is flushed every 256 points per thread (5^256 < DBL_MAX)
 #pragma unroll 1
     for (int base = 0; base < n; base += CHUNK) {
         const int stop = (n - base < CHUNK) ? n : base + CHUNK;
         double pl = 1.0;
-        int i = base + lane;
+        int i = base + Team<TW>::tid(lane);
 #pragma unroll 1
-        for (; i + 32 * (U - 1) < stop; i += 32 * U) {
+        for (; i + NT * (U - 1) < stop; i += NT * U) {
             double x[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) x[u] = xs[i + 32 * u];
+            for (int u = 0; u < U; u++) x[u] = xs[i + NT * u];
             accumulate_points<G, U>(x, prm, A, B, C, pl, hl);
         }
         if (U > 1) {
 #pragma unroll 1
-            for (; i < stop; i += 32) {
+            for (; i < stop; i += NT) {
                 double x[1] = {xs[i]};
                 accumulate_points<G, 1>(x, prm, A, B, C, pl, hl);
             }
@@ -439,7 +468,7 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
 }
 
 // MAP labels of the final z and their statistics: v[0,G) count, [G,2G) sum y, [2G,3G) sum y^2
-template <int G>
+template <int G, int TW>
 __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            const double* tab, double (&v)[16]) {
     const auto prm = load_params<G>(pm, tab);
@@ -447,7 +476,7 @@ __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n,
 #pragma unroll
     for (int k = 0; k < G; k++) { cnt[k] = 0.0; sy[k] = 0.0; syy[k] = 0.0; }
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) {
+    for (int i = Team<TW>::tid(lane); i < n; i += Team<TW>::NT) {
         double x = xs[i];
         int bk = map_label<G>(x, prm);
 #pragma unroll
@@ -467,23 +496,25 @@ __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n,
 #endif
 template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_MAXG) ? 2 : 1; };
 
+template <int TW>
 __device__ __noinline__ void estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
                                             const double* tab, double (&v)[16]) {
     switch (G) {
-        case 2: estep_pass<2, Unroll<2>::value>(xs, n, lane, pm, tab, v); break;
-        case 3: estep_pass<3, Unroll<3>::value>(xs, n, lane, pm, tab, v); break;
-        case 4: estep_pass<4, Unroll<4>::value>(xs, n, lane, pm, tab, v); break;
-        default: estep_pass<5, Unroll<5>::value>(xs, n, lane, pm, tab, v); break;
+        case 2: estep_pass<2, Unroll<2>::value, TW>(xs, n, lane, pm, tab, v); break;
+        case 3: estep_pass<3, Unroll<3>::value, TW>(xs, n, lane, pm, tab, v); break;
+        case 4: estep_pass<4, Unroll<4>::value, TW>(xs, n, lane, pm, tab, v); break;
+        default: estep_pass<5, Unroll<5>::value, TW>(xs, n, lane, pm, tab, v); break;
     }
 }
 
+template <int TW>
 __device__ __noinline__ void label_dispatch(int G, const double* xs, int n, int lane, const double* pm,
                                             const double* tab, double (&v)[16]) {
     switch (G) {
-        case 2: label_pass<2>(xs, n, lane, pm, tab, v); break;
-        case 3: label_pass<3>(xs, n, lane, pm, tab, v); break;
-        case 4: label_pass<4>(xs, n, lane, pm, tab, v); break;
-        default: label_pass<5>(xs, n, lane, pm, tab, v); break;
+        case 2: label_pass<2, TW>(xs, n, lane, pm, tab, v); break;
+        case 3: label_pass<3, TW>(xs, n, lane, pm, tab, v); break;
+        case 4: label_pass<4, TW>(xs, n, lane, pm, tab, v); break;
+        default: label_pass<5, TW>(xs, n, lane, pm, tab, v); break;
     }
 }
 
@@ -493,11 +524,15 @@ __device__ __noinline__ void label_dispatch(int G, const double* xs, int n, int 
 // One copy of this code serves every G: the scalar M-step runs once per warp with lane k owning
 // component k (lanes >= G shadow component 0), only the point loops are specialised on G.
 // ---------------------------------------------------------------------------------------------
+template <int TW>
 __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
-                                     double* pm, const double* tab, int extra_mstep) {
+                                     double* pm, const double* tab, double* red, int extra_mstep) {
+    typedef Team<TW> T;
     const double eps = DBL_EPSILON, rteps = 1.4901161193847656e-08, tol = 1e-5;
     const double dn = (double)n;
-    if (lane == 0) { row->valid = 0; row->iters = 0; }
+    const int tid = T::tid(lane);
+    const bool lead0 = T::lead() && lane == 0;
+    if (lead0) { row->valid = 0; row->iters = 0; }
     if (G > n) return;   // mclustBIC: G <- G[G <= n]
     const int kown = lane < G ? lane : 0;
     const bool owner = lane < G;
@@ -513,7 +548,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         double v[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = 0.0;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = tid; i < n; i += T::NT) {
             double x = xs[i];
             int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
 #pragma unroll
@@ -521,7 +556,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
                 if (k == cl) { v[k] += 1.0; v[GMAX + k] += x; }
             }
         }
-        double t = reduce16(v, lane);
+        double t = T::reduce(v, lane, red);
         double cnt = slot(t, kown), sx = slot(t, GMAX + kown);
         if (__any_sync(FULLMASK, owner && cnt <= rteps)) return;   // an empty class: "mixing proportion fell below threshold"
         mu_own = sx / cnt;
@@ -531,7 +566,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         double m4 = __shfl_sync(FULLMASK, mu_own, 4);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = 0.0;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = tid; i < n; i += T::NT) {
             double x = xs[i];
             int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
             double m = cl == 0 ? m0 : cl == 1 ? m1 : cl == 2 ? m2 : cl == 3 ? m3 : m4;
@@ -542,7 +577,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
                 if (k == cl) v[k] += dd;
             }
         }
-        t = reduce16(v, lane);
+        t = T::reduce(v, lane, red);
         sig_own = slot(t, kown) / cnt;
     }
 
@@ -555,12 +590,12 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         nh_own = -0.5 / sig_own;
         lc_own = log(pro_own) - 0.5 * (PI2LOG + log(sig_own));
         iter++;
-        __syncwarp();
-        if (owner) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
-        __syncwarp();
+        T::sync();
+        if (owner && T::lead()) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
+        T::sync();
         double v[16];
-        estep_dispatch(G, xs, n, lane, pm, tab, v);
-        double t = reduce16(v, lane);
+        estep_dispatch<TW>(G, xs, n, lane, pm, tab, v);
+        double t = T::reduce(v, lane, red);
         A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
         hood = slot(t, 3 * G);
         double err = fabs(hold - hood) / (1.0 + fabs(hood));
@@ -576,8 +611,8 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         sig_own = fma(-dm, dm, C * ra);
         pro_own = A / dn;
     }
-    if (lane == 0) {
-        // work counters (per warp, shared memory): iterations executed, points x components, points
+    if (lead0) {
+        // work counters (per team, shared memory): iterations executed, points x components, points
         st->em_iters += (double)iter;
         st->triples += dn * (double)G * (double)iter;
         st->point_iters += dn * (double)iter;
@@ -606,10 +641,10 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
     }
     // MAP labels from the final z (same parameters as the last E-step) and their statistics
     double v[16];
-    label_dispatch(G, xs, n, lane, pm, tab, v);   // pm still holds the parameters of the last E-step
-    double t = reduce16(v, lane);
+    label_dispatch<TW>(G, xs, n, lane, pm, tab, v);   // pm still holds the parameters of the last E-step
+    double t = T::reduce(v, lane, red);
     double cnt = slot(t, kown), sy = slot(t, G + kown), syy = slot(t, 2 * G + kown);
-    if (owner) {
+    if (owner && T::lead()) {
         row->mean[lane] = mean_out;
         row->sigsq[lane] = sig_out;
         row->mu_em[lane] = mu_own;
@@ -619,7 +654,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         row->sy[lane] = sy;
         row->syy[lane] = syy;
     }
-    if (lane == 0) {
+    if (lead0) {
         row->loglik = hood;
         row->bic = 2.0 * hood - (double)(3 * G - 1) * log(dn);
         row->valid = 1;
@@ -627,19 +662,27 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
 }
 
 // G = 1 row: mvn1d closed form
-__device__ __forceinline__ void fit_row1(const double* xs, int n, int lane, Row* row) {
-    double a[2] = {0.0, 0.0};
-    for (int i = lane; i < n; i += 32) { double x = xs[i]; a[0] += x; a[1] = fma(x, x, a[1]); }
-    warp_sum_vec<2>(a);
+template <int TW>
+__device__ __forceinline__ void fit_row1(const double* xs, int n, int lane, Row* row, double* red) {
+    typedef Team<TW> T;
+    const int tid = T::tid(lane);
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+    for (int i = tid; i < n; i += T::NT) { double x = xs[i]; v[0] += x; v[1] = fma(x, x, v[1]); }
+    double t = T::reduce(v, lane, red);
+    const double sx = slot(t, 0), sxx = slot(t, 1);
     double dn = (double)n;
-    double mu = a[0] / dn;
-    double ss = 0.0;
-    for (int i = lane; i < n; i += 32) { double t = xs[i] - mu; ss = fma(t, t, ss); }
-    ss = warp_sum(ss) / dn;
-    if (lane == 0) {
+    double mu = sx / dn;
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+    for (int i = tid; i < n; i += T::NT) { double d = xs[i] - mu; v[0] = fma(d, d, v[0]); }
+    t = T::reduce(v, lane, red);
+    const double ss = slot(t, 0) / dn;
+    if (T::lead() && lane == 0) {
         row->iters = 0;
         row->mean[0] = mu; row->sigsq[0] = ss;
-        row->cnt[0] = dn; row->sy[0] = a[0]; row->syy[0] = a[1];
+        row->cnt[0] = dn; row->sy[0] = sx; row->syy[0] = sxx;
         row->mu_em[0] = mu; row->nh_em[0] = 0.0; row->lc_em[0] = 0.0;
         if (ss == 0.0) { row->valid = 0; }
         else {
@@ -873,11 +916,13 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
 // ---------------------------------------------------------------------------------------------
 // The whole fit-set on a sorted slab.  Returns the selected number of components (0 = failed).
 // ---------------------------------------------------------------------------------------------
+template <int TW>
 __device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* rows, const DevCfg& cfg, WarpStats* st,
-                                       double* pm, const double* tab) {
-    fit_row1(xs, n, lane, &rows[0]);
-    for (int G = 2; G <= GMAX; G++) fit_row(G, xs, n, lane, &rows[G - 1], st, pm, tab, cfg.extra_mstep);
-    __syncwarp();
+                                       double* pm, const double* tab, double* red) {
+    typedef Team<TW> T;
+    fit_row1<TW>(xs, n, lane, &rows[0], red);
+    for (int G = 2; G <= GMAX; G++) fit_row<TW>(G, xs, n, lane, &rows[G - 1], st, pm, tab, red, cfg.extra_mstep);
+    T::sync();
     // near-tie diagnostic: two best BICs within 1e-9 relative
     bool bic_near = false;
     {
@@ -889,12 +934,30 @@ __device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* r
         if (b2 > -INFINITY && fabs(b1 - b2) <= 1e-9 * fabs(b1)) bic_near = true;
     }
     int comps = restricted_select(rows, n, cfg);
-    if (lane == 0) {
+    if (T::lead() && lane == 0) {
         st->fit_sets += 1.0;
         if (bic_near) st->bic_near += 1.0;
         if (comps == 0) st->failed_sets += 1.0;
     }
     return comps;
+}
+
+// in-place ascending bitonic sort of np (power of two) doubles by a team
+template <int TW>
+__device__ __forceinline__ void team_sort(double* xs, int np, int lane) {
+    typedef Team<TW> T;
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = T::tid(lane); t < (np >> 1); t += T::NT) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int l = i | j;
+                bool up = ((i & k) == 0);
+                double a = xs[i], b = xs[l];
+                if ((a > b) == up) { xs[i] = b; xs[l] = a; }
+            }
+            T::sync();
+        }
+    }
 }
 
 }  // namespace scdd

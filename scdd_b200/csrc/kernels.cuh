@@ -253,6 +253,7 @@ struct FitArgs {
     int perm_b0;               // first permutation of this launch inside `perm`
     int ngenes, nb, sets;      // sets per (gene, permutation): 2 = (c1, c2), 3 = (c1, c2, oa)
     int np_max;                // slab capacity (power of two)
+    double* xs_global;         // CTA teams only: per-CTA slabs in global memory when np_max exceeds shared memory
     double* jp;                // [ngenes * nb * sets] log joint posterior of each fit-set
     scdd_fit* fits;            // observed-data detail outputs (nullable): [3 * ngenes] as (oa, c1, c2)
     int32_t* cls_oa;
@@ -283,30 +284,53 @@ __device__ __noinline__ int label_of(const Row& r, double x) {
 #define SCDD_FIT_WARPS 16
 #endif
 constexpr int FIT_MAX_WARPS = SCDD_FIT_WARPS;
-__host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
-    return (size_t)np * sizeof(double) + 4 * GMAX * sizeof(double) + GMAX * sizeof(Row) + sizeof(WarpStats);
-}
+constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
+constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;    // larger fit-sets are run by a whole CTA
 
+// per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
+// scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
+__host__ __device__ constexpr size_t fit_region_head(int tw) {
+    return 4 * GMAX * sizeof(double) + GMAX * sizeof(Row) + sizeof(WarpStats) + (tw > 1 ? (size_t)tw * 16 * sizeof(double) : 0);
+}
+__host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
+    return fit_region_head(1) + (size_t)np * sizeof(double);
+}
+static_assert(fit_region_head(1) % 16 == 0 && fit_region_head(FIT_CTA_WARPS) % 16 == 0, "xs must stay 16-byte aligned");
+
+template <int TW>
 __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
+    typedef Team<TW> T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = fit_smem_per_warp(a.np_max);
+    const int tid = T::tid(lane);
     double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/32), shared by the CTA
     if (threadIdx.x < 32) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
     __syncthreads();
-    double* xs = reinterpret_cast<double*>(smem_raw + 256 + warp * per_warp);
-    double* pm = xs + a.np_max;                       // {mu, nh, lc, pad} x GMAX, 16-byte aligned
+    unsigned char* region = smem_raw + 256 + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
+    double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
     Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
-    if (lane == 0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
-    __syncwarp();
+    double* red = reinterpret_cast<double*>(st + 1);
+    double* xs = (TW > 1 && a.xs_global) ? a.xs_global + (size_t)blockIdx.x * a.np_max
+                                         : reinterpret_cast<double*>(region + fit_region_head(TW));
+    const bool lead0 = T::lead() && lane == 0;
+    if (lead0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    T::sync();
     const long long total = (long long)a.ngenes * a.nb * a.sets;
     const double NaN = nan("");
 
     for (;;) {
         long long item = 0;
-        if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ULL);
-        item = __shfl_sync(FULLMASK, item, 0);
+        if (TW == 1) {
+            if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ULL);
+            item = __shfl_sync(FULLMASK, item, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) *reinterpret_cast<long long*>(red) = (long long)atomicAdd(a.work_counter, 1ULL);
+            __syncthreads();
+            item = *reinterpret_cast<long long*>(red);
+            __syncthreads();
+        }
         if (item >= total) break;
         const int w = (int)(item % a.sets);
         const long long u = item / a.sets;
@@ -323,7 +347,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
         // ---- gather the (permuted) subset into the slab, pad to a power of two, sort ----
         int np = 2;
         while (np < n) np <<= 1;
-        for (int j = lane; j < np; j += 32) {
+        for (int j = tid; j < np; j += T::NT) {
             double v = INFINITY;
             if (j < n) {
                 uint32_t i = a.part[o + pofs + j];
@@ -333,20 +357,20 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             }
             xs[j] = v;
         }
-        __syncwarp();
-        warp_sort(xs, np, lane);
+        T::sync();
+        team_sort<TW>(xs, np, lane);
 
         double jp = NaN;
         int comps = 0;
         if (n < 1 || xs[0] == xs[n - 1]) {
             // all values identical: the reference jitters with runif() (R/mclust.restricted.R:48-50),
             // which consumes RNG state mid-stream; reported, never silently fitted
-            if (lane == 0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
+            if (lead0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
         } else {
-            comps = fit_set(xs, n, lane, rows, a.cfg, st, pm, tab);
+            comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, tab, red);
             if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
         }
-        if (lane == 0) a.jp[item] = jp;
+        if (lead0) a.jp[item] = jp;
 
         // ---- observed-data detail: the list mclustRestricted returns ----
         if (a.fits) {
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             if (comps > 0) {
                 const Row& mc = rows[comps - 1];
                 if (comps > 1) mean_order(mc, comps, ord);
-                if (lane == 0) {
+                if (lead0) {
                     f->G = comps; f->model_v = comps > 1; f->n = n; f->df = comps > 1 ? 3 * comps - 1 : 2;
                     f->bic = mc.bic; f->loglik = mc.loglik;
                     for (int k = 0; k < GMAX; k++) {
@@ -364,7 +388,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
                         f->var[k] = k < comps ? mc.sigsq[ord[k]] : NaN;
                     }
                 }
-                for (int j = lane; j < n; j += 32) {
+                for (int j = tid; j < n; j += T::NT) {
                     uint32_t i = a.part[o + pofs + j];
                     double x = a.vals[o + perm_lookup(a, o, ng, b, i)];
                     int l = 0;
@@ -378,19 +402,19 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
                     cls[o + i] = (comps > 1 ? ord[l] : l) + 1;   // R/mclust.restricted.R:243-247
                 }
             } else {
-                if (lane == 0) {
+                if (lead0) {
                     f->G = 0; f->model_v = 0; f->n = n; f->df = 0; f->bic = NaN; f->loglik = NaN;
                     for (int k = 0; k < GMAX; k++) { f->mean[k] = NaN; f->var[k] = NaN; }
                 }
-                for (int j = lane; j < n; j += 32) cls[o + a.part[o + pofs + j]] = 0;
+                for (int j = tid; j < n; j += T::NT) cls[o + a.part[o + pofs + j]] = 0;
             }
         }
-        __syncwarp();
+        T::sync();
     }
 
     // ---- flush the work counters ----
-    __syncwarp();
-    if (lane == 0) {
+    T::sync();
+    if (lead0) {
         double v[9] = {st->triples, st->point_iters, st->em_iters, st->cap_hits, st->tol_near,
                        st->bic_near, st->const_sets, st->failed_sets, st->fit_sets};
 #pragma unroll
@@ -426,10 +450,11 @@ __device__ __forceinline__ uint64_t orderable(double v) {
 
 __global__ void ks_kernel(const double* __restrict__ vals, const int64_t* __restrict__ off,
                           const uint32_t* __restrict__ part, const int32_t* __restrict__ n1, int ngenes,
-                          int np_max, double* __restrict__ D) {
+                          int np_max, double* __restrict__ D, uint64_t* key_global, uint32_t* idx_global) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* idx = reinterpret_cast<uint32_t*>(key + np_max);
+    // genes too long for shared memory are sorted in a per-CTA global (L2-resident) slab
+    uint64_t* key = key_global ? key_global + (size_t)blockIdx.x * np_max : reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* idx = idx_global ? idx_global + (size_t)blockIdx.x * np_max : reinterpret_cast<uint32_t*>(key + np_max);
     for (int g = blockIdx.x; g < ngenes; g += gridDim.x) {
         int64_t o = off[g];
         int n = (int)(off[g + 1] - o);

@@ -276,29 +276,48 @@ struct Pipeline {
     size_t idx_bytes() const { return wide_idx ? 4 : 2; }
 
     // launches the persistent fit kernel over ngenes x nb x sets fit-sets
+    DevBuf<double> d_xs_scratch;
     void launch_fit(cudaStream_t s, FitArgs a, int nmax_points) {
         int np = 2;
         while (np < nmax_points) np <<= 1;
-        const size_t per_warp = fit_smem_per_warp(np);
-        const size_t smem_cap = 227 * 1024 - 256;   // 256 B: the CTA's 2^(j/32) table
-        int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
-        if (warps < 1)
-            throw ScddError{SCDD_ERR_TOO_LARGE, "a fit-set of " + std::to_string(nmax_points) +
-                            " points does not fit the shared-memory slab of the warp-per-fit kernel"};
         const long long total = (long long)a.ngenes * a.nb * a.sets;
         if (total == 0) return;
-        const size_t smem = per_warp * warps + 256;
-        CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        long long want = (total + warps - 1) / warps;
-        int grid = (int)std::min<long long>(n_sm, want);
+        const size_t smem_cap = 227 * 1024 - 256;   // 256 B: the CTA's 2^(j/32) table
         a.np_max = np;
         a.work_counter = d_counter.p;
         a.stats = d_stats.p;
         a.cfg = cfg;
+        a.xs_global = nullptr;
+        int grid, threads;
+        size_t smem;
+        const bool warp_team = nmax_points <= FIT_WARP_TEAM_MAX_POINTS;
+        if (warp_team) {
+            const size_t per_warp = fit_smem_per_warp(np);
+            int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
+            smem = per_warp * warps + 256;
+            threads = warps * 32;
+            grid = (int)std::min<long long>(n_sm, (total + warps - 1) / warps);
+            CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            // one CTA per fit-set; the vector stays in shared memory when it fits, else in an L2-resident slab
+            const size_t head = fit_region_head(FIT_CTA_WARPS);
+            threads = FIT_CTA_WARPS * 32;
+            grid = (int)std::min<long long>(n_sm, total);
+            if (head + (size_t)np * sizeof(double) <= smem_cap) {
+                smem = head + (size_t)np * sizeof(double) + 256;
+            } else {
+                smem = head + 256;
+                const size_t need = (size_t)grid * np;
+                if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
+                a.xs_global = d_xs_scratch.p;
+            }
+            CK(cudaFuncSetAttribute(fit_kernel<FIT_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         CK(cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), s));
         Timed t;
         if (time_kernels) t = tick_begin(0, s);
-        fit_kernel<<<grid, warps * 32, smem, s>>>(a);
+        if (warp_team) fit_kernel<1><<<grid, threads, smem, s>>>(a);
+        else fit_kernel<FIT_CTA_WARPS><<<grid, threads, smem, s>>>(a);
         CK(cudaGetLastError());
         if (time_kernels) tick_end(t, s);
         fit_launches += 1;
@@ -740,17 +759,25 @@ int32_t scdd_ks(const double* vals, const int64_t* gene_off, const int32_t* cond
             int np = 2;
             while (np < P.max_n) np <<= 1;
             size_t smem = (size_t)np * 12;
-            if (smem > 227 * 1024)
-                throw ScddError{SCDD_ERR_TOO_LARGE, "KS: a gene with " + std::to_string(P.max_n) + " cells exceeds the shared-memory sort"};
             DevBuf<double> d_D;
+            DevBuf<uint64_t> d_key;
+            DevBuf<uint32_t> d_idx;
             d_D.alloc(ngenes);
-            CK(cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / std::max<size_t>(smem, 1)));
-            int grid = std::min(ngenes, P.n_sm * per_sm);
+            int grid;
+            if (smem <= 200 * 1024) {
+                CK(cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / std::max<size_t>(smem, 1)));
+                grid = std::min(ngenes, P.n_sm * per_sm);
+            } else {
+                grid = std::min(ngenes, P.n_sm * 2);
+                d_key.alloc((size_t)grid * np);
+                d_idx.alloc((size_t)grid * np);
+                smem = 0;
+            }
             cudaEvent_t t0, t1;
             CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
             CK(cudaEventRecord(t0, s));
-            ks_kernel<<<grid, 128, smem, s>>>(P.d_logy.p, P.d_off.p, P.d_part.p, P.d_n1.p, ngenes, np, d_D.p);
+            ks_kernel<<<grid, smem ? 128 : 512, smem, s>>>(P.d_logy.p, P.d_off.p, P.d_part.p, P.d_n1.p, ngenes, np, d_D.p, d_key.p, d_idx.p);
             CK(cudaGetLastError());
             CK(cudaEventRecord(t1, s));
             CK(cudaMemcpyAsync(D, d_D.p, ngenes * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -218,3 +218,44 @@ def test_scdd_api_end_to_end(golden_dir):
     assert np.array_equal(api.results(out3, "Genes")["nonzero.pvalue"], op)
     ks = api.testKS(X, cond, inclZero=False, numDE=20, DEIndex=np.arange(1, 21))
     assert set(ks.keys()) == {"genes", "p", "p.unadj", "power", "fdr"} and 0 <= ks["power"] <= 1
+
+
+def _big_genes(sizes, seed=5):
+    rng = np.random.default_rng(seed)
+    rows, conds = [], []
+    for n in sizes:
+        a = rng.normal(2.0, 0.7, size=int(n * 0.6))
+        b = rng.normal(4.5, 0.5, size=n - a.size)
+        v = np.concatenate([a, b])
+        rng.shuffle(v)
+        rows.append(v)
+        conds.append((rng.random(n) < 0.5).astype(np.int32))
+    off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.int64)
+    return np.concatenate(rows), np.concatenate(conds), off
+
+
+def test_large_fit_sets_cta_team():
+    """fit-sets above the warp slab (config 5 scale): CTA-per-fit-set variant, shared and global-memory slabs"""
+    logy, c01, off = _big_genes([2600, 5000, 9000, 40000])
+    fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
+    ofits, ocls_oa, ocls_c, obf, oden = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    for g in range(off.size - 1):
+        for w in range(3):
+            assert fits[g, w]["G"] == ofits[g][w]["G"], (g, w)
+            np.testing.assert_allclose(fits[g, w]["bic"], ofits[g][w]["bic"], rtol=RTOL)
+            np.testing.assert_allclose(fits[g, w]["mean"][:ofits[g][w]["G"]], ofits[g][w]["mean"], rtol=1e-7)
+    assert np.array_equal(cls_oa, ocls_oa) and np.array_equal(cls_c, ocls_c)
+    np.testing.assert_allclose(bf, obf, rtol=RTOL)
+    np.testing.assert_allclose(den, oden, rtol=RTOL)
+
+
+def test_large_genes_permutations_and_ks():
+    logy, c01, off = _big_genes([3000, 6000, 70000], seed=9)
+    ng = off.size - 1
+    seeds = hp.gene_seeds(11, ng)
+    out, st = hp.perm_bf(logy, c01, off, 2, seed6=seeds, cfg=hp.make_cfg(**PRIORS))
+    ref = po.perm_batch(logy, c01, off, 2, seed6=seeds, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out, ref, rtol=RTOL)
+    D, p = hp.ks(np.exp(logy), c01, off)
+    oD, op = po.ks_batch(np.exp(logy), c01, off)
+    assert np.array_equal(D, oD) and np.array_equal(p, op)
