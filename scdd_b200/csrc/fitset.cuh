@@ -196,6 +196,19 @@ __device__ __forceinline__ double rcp_sum(double x) {
 #endif
 }
 
+// 1/x for positive normal x (M-step scalars): same seed + two Newton steps; within 1 ulp.  Used instead of the
+// IEEE division of the reference's Fortran (a rounding-level difference) because nvcc's correctly rounded
+// fp64 division is a ~60-instruction subroutine call on the per-iteration critical path of every warp.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // exp() arguments below mclust's SMALOG = -708 give exactly 0 (as in the reference).  The test is made on
 // the high word (a <= 0 here) so that no fp64-pipe instruction is spent on it, and applied to the
 // result so that it stays off the dependency chain of the polynomial.
@@ -212,9 +225,11 @@ __device__ __forceinline__ void exp_neg_vec(const double (&a)[N], double (&e)[N]
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_TAB_CONST[1], a[i]);
+    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_TAB_CONST[2], r[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[2], r[i]);
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[3], r[i], EXP_TAB_CONST[4]);
 #pragma unroll
@@ -240,9 +255,11 @@ __device__ __forceinline__ void exp_neg_vec(const double (&a)[N], double (&e)[N]
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_RED[0], MAGIC);
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_RED[1], a[i]);
+    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(t[i] - MAGIC, EXP_RED[2], r[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_RED[1], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_RED[2], r[i]);
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(EXP_POLY[0], r[i], EXP_POLY[1]);
 #pragma unroll
@@ -281,38 +298,58 @@ struct ParamsSmem {
 
 // U points x G components: unnormalised responsibilities e = exp(t - max t), d = x - mu, q = d^2,
 // per point S = sum_k e and the max.
+// max / sum of G values as a balanced tree (dependency depth ceil(log2 G) instead of G - 1)
+template <int G>
+__device__ __forceinline__ double tree_max(const double* a) {
+    if (G == 1) return a[0];
+    if (G == 2) return (a[1] > a[0]) ? a[1] : a[0];
+    if (G == 3) { double m = (a[1] > a[0]) ? a[1] : a[0]; return (a[2] > m) ? a[2] : m; }
+    double m01 = (a[1] > a[0]) ? a[1] : a[0];
+    double m23 = (a[3] > a[2]) ? a[3] : a[2];
+    double m = (m23 > m01) ? m23 : m01;
+    if (G == 5) m = (a[4] > m) ? a[4] : m;
+    return m;
+}
+template <int G>
+__device__ __forceinline__ double tree_sum(const double* e) {
+    if (G == 1) return e[0];
+    if (G == 2) return __dadd_rn(e[0], e[1]);
+    if (G == 3) return __dadd_rn(__dadd_rn(e[0], e[1]), e[2]);
+    double s = __dadd_rn(__dadd_rn(e[0], e[1]), __dadd_rn(e[2], e[3]));
+    if (G == 5) s = __dadd_rn(s, e[4]);
+    return s;
+}
+
 template <int G, int U, class P>
 __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
                                              double (&q)[U * G], double (&S)[U], double (&tmax)[U]) {
-    double a[U * G];
+    // written column-wise (all d, then all q, then all t): the in-order warp then always has U*G independent
+    // fp64 instructions between an operation and its consumer
+    double a[U * G], h[G], l[G];
 #pragma unroll
     for (int k = 0; k < G; k++) {
-        double m, h, l;
-        prm.get(k, m, h, l);
+        double m;
+        prm.get(k, m, h[k], l[k]);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            d[u * G + k] = __dsub_rn(x[u], m);
-            q[u * G + k] = __dmul_rn(d[u * G + k], d[u * G + k]);
-            a[u * G + k] = fma(q[u * G + k], h, l);
-        }
+        for (int u = 0; u < U; u++) d[u * G + k] = __dsub_rn(x[u], m);
     }
 #pragma unroll
+    for (int i = 0; i < U * G; i++) q[i] = __dmul_rn(d[i], d[i]);
+#pragma unroll
     for (int u = 0; u < U; u++) {
-        double m = a[u * G];
 #pragma unroll
-        for (int k = 1; k < G; k++) m = (a[u * G + k] > m) ? a[u * G + k] : m;
-        tmax[u] = m;
+        for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
+    }
 #pragma unroll
-        for (int k = 0; k < G; k++) a[u * G + k] = __dsub_rn(a[u * G + k], m);
+    for (int u = 0; u < U; u++) tmax[u] = tree_max<G>(&a[u * G]);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int k = 0; k < G; k++) a[u * G + k] = __dsub_rn(a[u * G + k], tmax[u]);
     }
     exp_neg_vec<U * G>(a, e, prm.tab);
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        double s = e[u * G];
-#pragma unroll
-        for (int k = 1; k < G; k++) s = __dadd_rn(s, e[u * G + k]);
-        S[u] = s;
-    }
+    for (int u = 0; u < U; u++) S[u] = tree_sum<G>(&e[u * G]);
 }
 
 // map(z): first index of the row maximum of z = e / S
@@ -496,26 +533,31 @@ __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n,
 #endif
 template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_MAXG) ? 2 : 1; };
 
+// returns the team total of slot (lane >> 1): the 16 partial sums never leave registers
 template <int TW>
-__device__ __noinline__ void estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
-                                            const double* tab, double (&v)[16]) {
+__device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
+                                              const double* tab, double* red) {
+    double v[16];
     switch (G) {
         case 2: estep_pass<2, Unroll<2>::value, TW>(xs, n, lane, pm, tab, v); break;
         case 3: estep_pass<3, Unroll<3>::value, TW>(xs, n, lane, pm, tab, v); break;
         case 4: estep_pass<4, Unroll<4>::value, TW>(xs, n, lane, pm, tab, v); break;
         default: estep_pass<5, Unroll<5>::value, TW>(xs, n, lane, pm, tab, v); break;
     }
+    return Team<TW>::reduce(v, lane, red);
 }
 
 template <int TW>
-__device__ __noinline__ void label_dispatch(int G, const double* xs, int n, int lane, const double* pm,
-                                            const double* tab, double (&v)[16]) {
+__device__ __noinline__ double label_dispatch(int G, const double* xs, int n, int lane, const double* pm,
+                                              const double* tab, double* red) {
+    double v[16];
     switch (G) {
         case 2: label_pass<2, TW>(xs, n, lane, pm, tab, v); break;
         case 3: label_pass<3, TW>(xs, n, lane, pm, tab, v); break;
         case 4: label_pass<4, TW>(xs, n, lane, pm, tab, v); break;
         default: label_pass<5, TW>(xs, n, lane, pm, tab, v); break;
     }
+    return Team<TW>::reduce(v, lane, red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -584,32 +626,34 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
     double hold = 8.988465674311579e307, hood = 0.0;   // "previous" log-likelihood sentinel (FLMAX/2 in mclust)
     int iter = 0;
     double A = 0.0, B = 0.0, C = 0.0, nh_own = 0.0, lc_own = 0.0;
+    const double inv_n = 1.0 / dn;
     bool failed = false, near_tol = false, capped = false;
     for (;;) {
         if (__any_sync(FULLMASK, owner && sig_own <= eps)) { failed = true; break; }   // "sigma-squared falls below threshold"
-        nh_own = -0.5 / sig_own;
-        lc_own = log(pro_own) - 0.5 * (PI2LOG + log(sig_own));
+        // E-step constants of the owned component: nh = -1/(2 sigsq), lc = log(pro) - (log 2pi + log sigsq)/2
+        const double rsig = fast_rcp(sig_own);
+        nh_own = -0.5 * rsig;
+        lc_own = 0.5 * log(pro_own * pro_own * rsig) - 0.5 * PI2LOG;
         iter++;
         T::sync();
         if (owner && T::lead()) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
         T::sync();
-        double v[16];
-        estep_dispatch<TW>(G, xs, n, lane, pm, tab, v);
-        double t = T::reduce(v, lane, red);
+        const double t = estep_dispatch<TW>(G, xs, n, lane, pm, tab, red);
         A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
         hood = slot(t, 3 * G);
-        double err = fabs(hold - hood) / (1.0 + fabs(hood));
+        // stop when |hold - hood| / (1 + |hood|) <= tol  (tested in product form: no division on the critical path)
+        const double diff = fabs(hold - hood), bound = tol * (1.0 + fabs(hood));
         hold = hood;
-        if (fabs(err - tol) <= 1e-7 * tol) near_tol = true;
-        if (!(err > tol)) break;
+        if (fabs(diff - bound) <= 1e-7 * bound) near_tol = true;
+        if (!(diff > bound)) break;
         if (iter >= EM_ITER_CAP) { capped = true; break; }
         // ---- M-step (lane k: component k) ----
         if (__any_sync(FULLMASK, owner && A <= rteps)) { failed = true; break; }
-        double ra = 1.0 / A;
-        double dm = B * ra;
+        const double ra = fast_rcp(A);
+        const double dm = B * ra;
         mu_own = mu_own + dm;
         sig_own = fma(-dm, dm, C * ra);
-        pro_own = A / dn;
+        pro_own = A * inv_n;
     }
     if (lead0) {
         // work counters (per team, shared memory): iterations executed, points x components, points
@@ -626,23 +670,21 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
     double mean_out = mu_own, sig_out = sig_own;
     if (extra_mstep) {
         // summaryMclustBIC: if sum((pro - colMeans(z))^2) > sqrt(eps) replace $parameters by one more M-step
-        double cm = A / dn;
+        double cm = A * inv_n;
         double term = owner ? (pro_own - cm) * (pro_own - cm) : 0.0;
         double dev = 0.0;
 #pragma unroll
         for (int k = 0; k < GMAX; k++) dev += __shfl_sync(FULLMASK, term, k);
         bool ok = !__any_sync(FULLMASK, owner && !(A > 0.0));
         if (dev > rteps && ok) {
-            double ra = 1.0 / A;
+            double ra = fast_rcp(A);
             double dm = B * ra;
             mean_out = mu_own + dm;
             sig_out = fma(-dm, dm, C * ra);
         }
     }
     // MAP labels from the final z (same parameters as the last E-step) and their statistics
-    double v[16];
-    label_dispatch<TW>(G, xs, n, lane, pm, tab, v);   // pm still holds the parameters of the last E-step
-    double t = T::reduce(v, lane, red);
+    const double t = label_dispatch<TW>(G, xs, n, lane, pm, tab, red);   // pm still holds the last E-step's parameters
     double cnt = slot(t, kown), sy = slot(t, G + kown), syy = slot(t, 2 * G + kown);
     if (owner && T::lead()) {
         row->mean[lane] = mean_out;

@@ -1,0 +1,55 @@
+// The real EM code (fit_row<1>, all G) run back to back on a fixed sorted vector per warp: separates the cost
+// of the EM iterations themselves from the per-fit-set work around them (gather, sort, selection, PPM score).
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include <random>
+#include <cuda_runtime.h>
+#include "../../scdd_b200/csrc/kernels.cuh"
+using namespace scdd;
+__global__ void __launch_bounds__(512, 1) k(const double* src, int n, int np, int reps, double* out, double* counters, int gonly) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    if (threadIdx.x < 32) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    __syncthreads();
+    unsigned char* region = smem_raw + 256 + warp * fit_smem_per_warp(np);
+    double* pm = reinterpret_cast<double*>(region);
+    Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
+    WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
+    double* red = reinterpret_cast<double*>(st + 1);
+    double* xs = reinterpret_cast<double*>(region + fit_region_head(1));
+    if (lane == 0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = lane; j < n; j += 32) xs[j] = src[j];
+    __syncwarp();
+    for (int r = 0; r < reps; r++) {
+        for (int G = 2; G <= GMAX; G++) {
+            if (gonly && G != gonly) continue;
+            fit_row<1>(G, xs, n, lane, &rows[G - 1], st, pm, tab, red, 1);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { atomicAdd(&counters[0], st->triples); atomicAdd(&counters[1], st->em_iters); out[blockIdx.x * 16 + warp] = rows[4].bic; }
+}
+int main() {
+    int n = 880, np = 1024;
+    std::mt19937 g(1); std::normal_distribution<double> nd(3.0, 1.0);
+    std::vector<double> h(n); for (auto& v : h) v = nd(g); std::sort(h.begin(), h.end());
+    double *d, *out, *cnt; cudaMalloc(&d, n * 8); cudaMalloc(&out, 148 * 16 * 8); cudaMalloc(&cnt, 16);
+    cudaMemcpy(d, h.data(), n * 8, cudaMemcpyHostToDevice);
+    size_t smem = 256 + 16 * fit_smem_per_warp(np);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int gonly : {0, 2, 3, 4, 5}) {
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        float best = 1e30f; double tr = 0, it = 0;
+        for (int r = 0; r < 3; r++) {
+            cudaMemset(cnt, 0, 16);
+            cudaEventRecord(a); k<<<148, 512, smem>>>(d, n, np, 20, out, cnt, gonly); cudaEventRecord(b); cudaEventSynchronize(b);
+            float ms; cudaEventElapsedTime(&ms, a, b); if (r && ms < best) best = ms;
+            double c[2]; cudaMemcpy(c, cnt, 16, cudaMemcpyDeviceToHost); tr = c[0]; it = c[1];
+        }
+        printf("G=%d%s: %.2f ms, %.3e triples/s, %.0f EM iterations (%.1f per fit), err=%s\n", gonly, gonly ? "" : " (all)", best, tr / (best * 1e-3), it,
+               it / (148.0 * 16 * 20 * (gonly ? 1 : 4)), cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
