@@ -169,7 +169,6 @@ __device__ __noinline__ int qclass_breaks(const double* xs, int n, int k, double
 // ---------------------------------------------------------------------------------------------
 __device__ const double EXP_TABLE_GLOBAL[32] = SCDD_EXP_TABLE_INIT;
 // polynomial coefficients of the table-free exp (expp::C): constant-bank operands, fetched with LDCU.128
-__constant__ double EXP_RED[3] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
 __constant__ double EXP_TAB_CONST[7] = {46.16624130844683, -0.021660849392446835, -5.145609244655338e-14,
                                         1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
 __constant__ double EXP_POLY[10] = {
@@ -209,74 +208,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(y, e, y);
 }
 
-// exp() arguments below mclust's SMALOG = -708 give exactly 0 (as in the reference).  The test is made on
-// the high word (a <= 0 here) so that no fp64-pipe instruction is spent on it, and applied to the
-// result so that it stays off the dependency chain of the polynomial.
-__device__ __forceinline__ double zero_if_small(double a, int hi, int lo) {
-    const bool small = (unsigned)__double2hiint(a) > 0xC0862000u;
-    return __hiloint2double(small ? 0 : hi, small ? 0 : lo);
-}
-
-template <int N>
-__device__ __forceinline__ void exp_neg_vec(const double (&a)[N], double (&e)[N], const double* tab) {
-    double t[N], r[N], p[N];
-#if SCDD_EXP_TABLE
-    using namespace expc;
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[2], r[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[3], r[i], EXP_TAB_CONST[4]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[5]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[6]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], C2);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = p[i] * r[i];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        const int n = __double2loint(t[i]);
-        const double T = tab[n & 31];
-        const double v = fma(T, p[i], T);
-        e[i] = zero_if_small(a[i], __double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
-    }
-#else
-    using namespace expp;
-    const double MAGIC = expc::MAGIC;
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_RED[0], MAGIC);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_RED[1], a[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_RED[2], r[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_POLY[0], r[i], EXP_POLY[1]);
-#pragma unroll
-    for (int j = 2; j < 10; j++) {
-#pragma unroll
-        for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_POLY[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < N; i++)
-        e[i] = zero_if_small(a[i], __double2hiint(p[i]) + (__double2loint(t[i]) << 20), __double2loint(p[i]));
-#endif
-}
-
 // Component parameters in E-step form: mu_k, nh_k = -1/(2 sigsq_k), lc_k = log pro_k - (log 2 pi + log sigsq_k)/2.
 // ParamsReg keeps them in registers (3G doubles per lane); ParamsSmem re-reads them from the warp's
 // shared-memory block for every point (broadcast loads on the LSU pipe), which frees 6G registers for
@@ -298,18 +229,7 @@ struct ParamsSmem {
 
 // U points x G components: unnormalised responsibilities e = exp(t - max t), d = x - mu, q = d^2,
 // per point S = sum_k e and the max.
-// max / sum of G values as a balanced tree (dependency depth ceil(log2 G) instead of G - 1)
-template <int G>
-__device__ __forceinline__ double tree_max(const double* a) {
-    if (G == 1) return a[0];
-    if (G == 2) return (a[1] > a[0]) ? a[1] : a[0];
-    if (G == 3) { double m = (a[1] > a[0]) ? a[1] : a[0]; return (a[2] > m) ? a[2] : m; }
-    double m01 = (a[1] > a[0]) ? a[1] : a[0];
-    double m23 = (a[3] > a[2]) ? a[3] : a[2];
-    double m = (m23 > m01) ? m23 : m01;
-    if (G == 5) m = (a[4] > m) ? a[4] : m;
-    return m;
-}
+// sum of G values as a balanced tree (dependency depth ceil(log2 G) instead of G - 1)
 template <int G>
 __device__ __forceinline__ double tree_sum(const double* e) {
     if (G == 1) return e[0];
@@ -319,13 +239,32 @@ __device__ __forceinline__ double tree_sum(const double* e) {
     if (G == 5) s = __dadd_rn(s, e[4]);
     return s;
 }
+template <int G>
+__device__ __forceinline__ int tree_imax(const int* v) {
+    if (G == 1) return v[0];
+    if (G == 2) return max(v[0], v[1]);
+    if (G == 3) return max(max(v[0], v[1]), v[2]);
+    int m = max(max(v[0], v[1]), max(v[2], v[3]));
+    if (G == 5) m = max(m, v[4]);
+    return m;
+}
 
+constexpr double LN2_32 = 0.021660849392498290;   // ln(2)/32
+
+// U points x G components: responsibilities up to the common factor of their point.
+//   t_k = q_k nh_k + lc_k is the log of the k-th term.  The log-sum-exp shift is NOT max_k t_k but that maximum
+//   rounded to the exp grid: with N_k = rint(t_k * 32/ln2) (already needed for the range reduction) and
+//   M = max_k N_k, e_k = exp(t_k - M ln2/32) = 2^((N_k - M)/32) exp(r_k).  The shift therefore costs integer
+//   instructions only -- no fp64 compare and no fp64 subtraction per component -- and sum_k e_k lies in
+//   (0.97, 1.03 G].  log-sum-exp is shift invariant, so the result is the reference's up to rounding.
+//   Outputs: e (U*G), d = x - mu, q = d^2, S = sum_k e_k and the integer shift M per point.
 template <int G, int U, class P>
 __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
-                                             double (&q)[U * G], double (&S)[U], double (&tmax)[U]) {
-    // written column-wise (all d, then all q, then all t): the in-order warp then always has U*G independent
-    // fp64 instructions between an operation and its consumer
-    double a[U * G], h[G], l[G];
+                                             double (&q)[U * G], double (&S)[U], int (&M)[U]) {
+    using namespace expc;
+    constexpr int N = U * G;
+    double a[N], t[N], r[N], p[N], h[G], l[G];
+    int n[N];
 #pragma unroll
     for (int k = 0; k < G; k++) {
         double m;
@@ -334,20 +273,50 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int u = 0; u < U; u++) d[u * G + k] = __dsub_rn(x[u], m);
     }
 #pragma unroll
-    for (int i = 0; i < U * G; i++) q[i] = __dmul_rn(d[i], d[i]);
+    for (int i = 0; i < N; i++) q[i] = __dmul_rn(d[i], d[i]);
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
         for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) tmax[u] = tree_max<G>(&a[u * G]);
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        // low word of t = N (two's complement) while |t_k| < 2^24; log-terms below -2^24 saturate (they are "zero")
+        n[i] = ((unsigned)__double2hiint(a[i]) >= 0xC1700000u) ? -(1 << 30) : __double2loint(t[i]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&n[u * G]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[2], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[3], r[i], EXP_TAB_CONST[4]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[5]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[6]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = p[i] * r[i];
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int k = 0; k < G; k++) a[u * G + k] = __dsub_rn(a[u * G + k], tmax[u]);
+        for (int k = 0; k < G; k++) {
+            const int i = u * G + k;
+            const int D = max(n[i] - M[u], -1021 * 32);     // <= 0; terms the reference zeroes (below -708) become <= 4.5e-308
+            const double T = prm.tab[D & 31];
+            const double v = fma(T, p[i], T);
+            e[i] = __hiloint2double(__double2hiint(v) + ((D >> 5) << 20), __double2loint(v));
+        }
     }
-    exp_neg_vec<U * G>(a, e, prm.tab);
 #pragma unroll
     for (int u = 0; u < U; u++) S[u] = tree_sum<G>(&e[u * G]);
 }
@@ -356,8 +325,9 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 template <int G, class P>
 __device__ __forceinline__ int map_label(double x, const P& prm) {
     double xx[1] = {x};
-    double e[G], d[G], q[G], S[1], tmax[1];
-    estep_points<G, 1, P>(xx, prm, e, d, q, S, tmax);
+    double e[G], d[G], q[G], S[1];
+    int M[1];
+    estep_points<G, 1, P>(xx, prm, e, d, q, S, M);
     double rs = rcp_sum(S[0]);
     double best = __dmul_rn(e[0], rs);
     int bk = 0;
@@ -428,9 +398,10 @@ struct Team {
 // ---------------------------------------------------------------------------------------------
 template <int G, int U, class P>
 __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
-                                                  double (&C)[G], double& pl, double& hl) {
-    double e[U * G], d[U * G], q[U * G], S[U], tmax[U];
-    estep_points<G, U, P>(x, prm, e, d, q, S, tmax);
+                                                  double (&C)[G], double& pl, long long& hs) {
+    double e[U * G], d[U * G], q[U * G], S[U];
+    int M[U];
+    estep_points<G, U, P>(x, prm, e, d, q, S, M);
 #pragma unroll
     for (int u = 0; u < U; u++) {
         double rs = rcp_sum(S[u]);
@@ -441,8 +412,8 @@ __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P&
             B[k] = fma(z, d[u * G + k], B[k]);
             C[k] = fma(z, q[u * G + k], C[k]);
         }
-        pl *= S[u];      // sum_i log S_i is taken as the log of a running product (S in [1, G])
-        hl += tmax[u];
+        pl *= S[u];      // sum_i log S_i is taken as the log of a running product (S in (0.97, 1.03 G])
+        hs += M[u];      // the shifts are integers: summed exactly, off the fp64 pipe
     }
 }
 
@@ -475,6 +446,7 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
 #pragma unroll
     for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
     double hl = 0.0;
+    long long hs = 0;
     constexpr int CHUNK = 256 * NT;   // the running product is flushed every 256 points per thread (5^256 < DBL_MAX)
 #pragma unroll 1
     for (int base = 0; base < n; base += CHUNK) {
@@ -486,17 +458,18 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
             double x[U];
 #pragma unroll
             for (int u = 0; u < U; u++) x[u] = xs[i + NT * u];
-            accumulate_points<G, U>(x, prm, A, B, C, pl, hl);
+            accumulate_points<G, U>(x, prm, A, B, C, pl, hs);
         }
         if (U > 1) {
 #pragma unroll 1
             for (; i < stop; i += NT) {
                 double x[1] = {xs[i]};
-                accumulate_points<G, 1>(x, prm, A, B, C, pl, hl);
+                accumulate_points<G, 1>(x, prm, A, B, C, pl, hs);
             }
         }
         hl += log(pl);
     }
+    hl = fma((double)hs, LN2_32, hl);   // log-likelihood: sum_i log S_i + (ln2/32) sum_i M_i
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.0;
 #pragma unroll
