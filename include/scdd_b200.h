@@ -145,8 +145,10 @@ void scdd_plan_destroy(scdd_plan* plan);
 /* software x87 extended-precision accumulate used by the KS kernel, run on the host:
  * out[i] = (double)(long-double running sum of steps[0..i]) */
 int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out);
-/* the kernels' exp() on the host build of the same source: out[i] = exp(x[i]) for x in [-708, 0] */
+/* the kernels' exp arithmetic (host build of the same source, shift 0): out[i] = exp(x[i]) for x in [-708, 0] */
 int32_t scdd_selftest_exp(const double* x, int32_t n, double* out);
+/* softmax of G <= 5 log-terms exactly as the E-step evaluates it; logsumexp may be NULL */
+int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp);
 /* measured fp64 FMA throughput of the device (TFLOP/s, DFMA = 2 flop), used as the roofline denominator */
 double scdd_measure_fp64_peak(int32_t device, double* sm_clock_mhz_out);
 

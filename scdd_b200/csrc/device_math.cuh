@@ -14,117 +14,71 @@
 namespace scdd {
 
 // ---------------------------------------------------------------------------------------------
-// exp(a) for a in [-708, 0]  (the EM E-step only ever needs exp(t_k - max_k t_k); values below
-// mclust's SMALOG = -708 clamp are replaced by 0 by the caller, so no subnormal handling is needed).
-//
-// exp(a) = 2^k * 2^(j/32) * exp(r),  32 k + j = rint(a * 32/ln2),  r = a - (32 k + j) ln2/32 (two-term
-// Cody-Waite, |r| <= ln2/64), exp(r) - 1 by a degree-6 polynomial (truncation < 4e-18), 2^(j/32) from a
-// 32-entry table (shared memory on the device).  11 fp64 operations instead of the 15 of a table-free
-// degree-11 evaluation; the fp64 pipe is the bottleneck of the fit kernel.  Max error 0.9 ulp.
+// The E-step's softmax terms.  For the log-terms t_k of one point (k = 1..G) the kernels need
+// e_k = exp(t_k - shift) for ANY common shift that keeps the sum in range (log-sum-exp is shift invariant).
+//   N_k = rint(t_k * 64/ln2)                 (magic-number rounding; also the exp range reduction)
+//   M   = max_k N_k                          (integer max: the shift is M * ln2/64, the max rounded to the grid)
+//   r_k = t_k - N_k * c,  c = fl(ln2/64)     (ONE fma: the error N_k (ln2/64 - c) splits into M (..), common to all k
+//                                             and cancelled exactly when the log-likelihood adds the shift back as
+//                                             M * c with the same c, and (N_k - M)(..) <= 1e-16 for every term that matters)
+//   e_k = 2^((N_k - M)/64) * exp(r_k) = 2^(D >> 6) * T[D & 63] * (1 + s(r_k)),  D = N_k - M <= 0
+// s(r) = exp(r) - 1 by a degree-5 polynomial on |r| <= ln2/128 (truncation 3e-17), T = 64-entry table of 2^(j/64).
+// fp64 cost per term: 1 (t) + 1 (kf) + 1 (r) + 4 (polynomial) + 1 (s) + 1 (table fma) = 9; max, shift, table index
+// and 2^k scaling are integer instructions.  These helpers are the single source of the arithmetic: the kernels
+// issue them column-wise over the G (or 2G) terms of a point, the host self-test calls them term by term.
 // ---------------------------------------------------------------------------------------------
-#define SCDD_EXP_TABLE_INIT                                                                                   \
-    {1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924, \
-     1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,         \
-     1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,       \
-     1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,      \
-     1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,         \
-     1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,         \
-     1.9571441241754002}
+#define SCDD_EXP_TABLE_SIZE 64
+#define SCDD_EXP_TABLE_INIT {1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, 1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951}
 
 namespace expc {
-constexpr double L2E32 = 46.16624130844683;            // 32 / ln 2
+constexpr double L2E64 = 92.33248261689366;            // 64 / ln 2
 constexpr double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: rint() in the low mantissa bits
-constexpr double LN2_32_HI = 0.021660849392446835;     // ln2/32, low 17 mantissa bits zero
-constexpr double LN2_32_LO = 5.145609244655338e-14;
-constexpr double C2 = 0.5, C3 = 1.0 / 6.0, C4 = 1.0 / 24.0, C5 = 1.0 / 120.0, C6 = 1.0 / 720.0;
+constexpr double LN2_64 = 0.010830424696249145;        // fl(ln2 / 64)
+constexpr double C2 = 0.5, C3 = 1.0 / 6.0, C4 = 1.0 / 24.0, C5 = 1.0 / 120.0;
+constexpr int NSAT = -(1 << 30);                       // N of a log-term below -2^23 ("minus infinity")
+constexpr int DMIN = -1021 * 64;                       // smallest shift kept: 2^-1021 (the reference zeroes below e^-708)
 }  // namespace expc
 
-SCDD_HD double exp_neg_tab(double a, const double* tab) {
+SCDD_HD int hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+SCDD_HD int lo_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    int64_t b; std::memcpy(&b, &x, 8); return (int)(int32_t)(b & 0xffffffff);
+#endif
+}
+SCDD_HD double from_words(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; std::memcpy(&x, &b, 8); return x;
+#endif
+}
+
+SCDD_HD double term_t(double a) { return fma(a, expc::L2E64, expc::MAGIC); }
+// low word of t = N (two's complement) while |a| < 2^23; log-terms below -2^23 saturate
+SCDD_HD int term_n(double a, double t) { return ((unsigned)hi_word(a) >= 0xC1600000u) ? expc::NSAT : lo_word(t); }
+SCDD_HD double term_r(double a, double t) { return fma(t - expc::MAGIC, -expc::LN2_64, a); }
+SCDD_HD double term_s(double r) {
     using namespace expc;
-    double t = fma(a, L2E32, MAGIC);
-    double kf = t - MAGIC;
-    double r = fma(kf, -LN2_32_HI, a);
-    r = fma(kf, -LN2_32_LO, r);
-    double p = fma(C6, r, C5);
-    p = fma(p, r, C4);
+    double p = fma(C5, r, C4);
     p = fma(p, r, C3);
     p = fma(p, r, C2);
     p = fma(p, r, 1.0);
-    double s = p * r;                       // exp(r) - 1
-#if defined(__CUDA_ARCH__)
-    int n = __double2loint(t);
-    double T = tab[n & 31];
-    double v = fma(T, s, T);
-    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
-#else
-    int64_t tb;
-    std::memcpy(&tb, &t, 8);
-    int n = (int)(int32_t)(tb & 0xffffffff);
-    double T = tab[n & 31];
-    double v = std::fma(T, s, T);
-    int64_t vb;
-    std::memcpy(&vb, &v, 8);
-    vb += (int64_t)(n >> 5) << 52;
-    double out;
-    std::memcpy(&out, &vb, 8);
-    return out;
-#endif
+    return p * r;
 }
-
-// Table-free variant: exp(a) = 2^k * exp(r), k = rint(a*log2(e)), r = a - k*ln2 in [-ln2/2, ln2/2],
-// degree-11 polynomial from tools/gen_exp_poly.py (15 fp64 operations, no loads, max error 0.65 ulp).
-namespace expp {
-constexpr double L2E = 1.4426950408889634074;
-constexpr double LN2_HI = 6.93147180369123816490e-01;  // fdlibm split: low 21 bits of hi are zero
-constexpr double LN2_LO = 1.90821492927058770002e-10;
-constexpr double C[10] = {2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06,
-                          2.4801521295954376e-05, 0.00019841269863053618, 0.0013888888917213717,
-                          0.008333333333330062, 0.04166666666662413, 0.16666666666666669, 0.5000000000000001};
-}  // namespace expp
-
-SCDD_HD double exp_neg_poly(double a) {
-    using namespace expp;
-    const double MAGIC = expc::MAGIC;
-    double t = fma(a, L2E, MAGIC);
-    double kf = t - MAGIC;
-    double r = fma(kf, -LN2_HI, a);
-    r = fma(kf, -LN2_LO, r);
-    double p = fma(2.510038549551032e-08, r, 2.7620088445409746e-07);
-    p = fma(p, r, 2.7557268459997064e-06);
-    p = fma(p, r, 2.4801521295954376e-05);
-    p = fma(p, r, 0.00019841269863053618);
-    p = fma(p, r, 0.0013888888917213717);
-    p = fma(p, r, 0.008333333333330062);
-    p = fma(p, r, 0.04166666666662413);
-    p = fma(p, r, 0.16666666666666669);
-    p = fma(p, r, 0.5000000000000001);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-#if defined(__CUDA_ARCH__)
-    int k = __double2loint(t);
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-#else
-    int64_t tb, pb;
-    std::memcpy(&tb, &t, 8);
-    int k = (int)(int32_t)(tb & 0xffffffff);
-    std::memcpy(&pb, &p, 8);
-    pb += (int64_t)k << 52;
-    double out;
-    std::memcpy(&out, &pb, 8);
-    return out;
-#endif
-}
-
-#ifndef SCDD_EXP_TABLE
-#define SCDD_EXP_TABLE 1
-#endif
-SCDD_HD double exp_neg(double a, const double* tab) {
-#if SCDD_EXP_TABLE
-    return exp_neg_tab(a, tab);
-#else
-    (void)tab;
-    return exp_neg_poly(a);
-#endif
+SCDD_HD double term_e(double s, int n, int M, const double* tab) {
+    int D = n - M;
+    if (D < expc::DMIN) D = expc::DMIN;
+    const double T = tab[D & 63];
+    const double v = fma(T, s, T);
+    return from_words(hi_word(v) + ((D >> 6) << 20), lo_word(v));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -160,21 +160,9 @@ __device__ __noinline__ int qclass_breaks(const double* xs, int n, int k, double
     return nbr;
 }
 
-// ---------------------------------------------------------------------------------------------
-// E-step arithmetic for N = (points x components) independent arguments at once.
-// exp() is evaluated "column-wise": every step of the range reduction and of the Horner chain is issued
-// for all N arguments before the next step, so the in-order warp always has N independent DFMAs in
-// flight (ptxas keeps each scalar exp() as one serial dependency chain otherwise).
-// Every element goes through exactly the operation sequence of exp_neg() (device_math.cuh).
-// ---------------------------------------------------------------------------------------------
-__device__ const double EXP_TABLE_GLOBAL[32] = SCDD_EXP_TABLE_INIT;
-// polynomial coefficients of the table-free exp (expp::C): constant-bank operands, fetched with LDCU.128
-__constant__ double EXP_TAB_CONST[7] = {46.16624130844683, -0.021660849392446835, -5.145609244655338e-14,
-                                        1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
-__constant__ double EXP_POLY[10] = {
-    2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05,
-    0.00019841269863053618, 0.0013888888917213717, 0.008333333333330062, 0.04166666666662413,
-    0.16666666666666669, 0.5000000000000001};   // source of the per-CTA shared copy
+__device__ const double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;   // source of the per-CTA shared copy
+// constant-bank copies of device_math.cuh's expc:: constants (fetched with LDCU, no per-iteration immediates)
+__constant__ double EXP_TAB_CONST[6] = {92.33248261689366, -0.010830424696249145, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 
 // 1/S for S in [1, GMAX]: MUFU.RCP64H seed + two Newton steps (5 DFMA, <= 1 ulp).  No special-case
 // branch: the argument range is known, unlike for the general-purpose __drcp_rn.
@@ -183,12 +171,11 @@ __device__ __forceinline__ double rcp_sum(double x) {
 #define SCDD_FAST_RCP 1
 #endif
 #if SCDD_FAST_RCP
+    // the seed is good to ~2^-23, e + e^2 makes the step cubic (2^-69): one step reaches rounding level
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
     e = fma(e, e, e);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
     return fma(y, e, y);
 #else
     return __drcp_rn(x);
@@ -219,7 +206,7 @@ struct ParamsReg {
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
-    const double* tab;   // 2^(j/32) table (shared memory)
+    const double* tab;   // 2^(j/64) table (shared memory)
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
@@ -249,14 +236,9 @@ __device__ __forceinline__ int tree_imax(const int* v) {
     return m;
 }
 
-constexpr double LN2_32 = 0.021660849392498290;   // ln(2)/32
-
-// U points x G components: responsibilities up to the common factor of their point.
-//   t_k = q_k nh_k + lc_k is the log of the k-th term.  The log-sum-exp shift is NOT max_k t_k but that maximum
-//   rounded to the exp grid: with N_k = rint(t_k * 32/ln2) (already needed for the range reduction) and
-//   M = max_k N_k, e_k = exp(t_k - M ln2/32) = 2^((N_k - M)/32) exp(r_k).  The shift therefore costs integer
-//   instructions only -- no fp64 compare and no fp64 subtraction per component -- and sum_k e_k lies in
-//   (0.97, 1.03 G].  log-sum-exp is shift invariant, so the result is the reference's up to rounding.
+// U points x G components: softmax terms (device_math.cuh, "The E-step's softmax terms"), issued column-wise:
+// every step is emitted for all U*G terms before the next one, so the in-order warp always has U*G independent
+// fp64 instructions between an operation and its consumer (ptxas -O2/-O3 would re-serialise the chains).
 //   Outputs: e (U*G), d = x - mu, q = d^2, S = sum_k e_k and the integer shift M per point.
 template <int G, int U, class P>
 __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
@@ -280,26 +262,19 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);                 // term_t
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        // low word of t = N (two's complement) while |t_k| < 2^24; log-terms below -2^24 saturate (they are "zero")
-        n[i] = ((unsigned)__double2hiint(a[i]) >= 0xC1700000u) ? -(1 << 30) : __double2loint(t[i]);
-    }
+    for (int i = 0; i < N; i++) n[i] = term_n(a[i], t[i]);
 #pragma unroll
     for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&n[u * G]);
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                 // kf
+    for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[2], r[i]);
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], EXP_TAB_CONST[3]);      // term_s
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[3], r[i], EXP_TAB_CONST[4]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[5]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[6]);
+    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[4]);
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 0.5);
 #pragma unroll
@@ -309,13 +284,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            const int i = u * G + k;
-            const int D = max(n[i] - M[u], -1021 * 32);     // <= 0; terms the reference zeroes (below -708) become <= 4.5e-308
-            const double T = prm.tab[D & 31];
-            const double v = fma(T, p[i], T);
-            e[i] = __hiloint2double(__double2hiint(v) + ((D >> 5) << 20), __double2loint(v));
-        }
+        for (int k = 0; k < G; k++) e[u * G + k] = term_e(p[u * G + k], n[u * G + k], M[u], prm.tab);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) S[u] = tree_sum<G>(&e[u * G]);
@@ -469,7 +438,7 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         }
         hl += log(pl);
     }
-    hl = fma((double)hs, LN2_32, hl);   // log-likelihood: sum_i log S_i + (ln2/32) sum_i M_i
+    hl = fma((double)hs, expc::LN2_64, hl);   // log-likelihood: sum_i log S_i + c sum_i M_i, the SAME c as in term_r
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.0;
 #pragma unroll

@@ -285,7 +285,8 @@ __device__ __noinline__ int label_of(const Row& r, double x) {
 #endif
 constexpr int FIT_MAX_WARPS = SCDD_FIT_WARPS;
 constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
-constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;    // larger fit-sets are run by a whole CTA
+constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
+constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/64) table    // larger fit-sets are run by a whole CTA
 
 // per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
@@ -304,9 +305,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tid = T::tid(lane);
     double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/32), shared by the CTA
-    if (threadIdx.x < 32) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    if (threadIdx.x < SCDD_EXP_TABLE_SIZE) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
     __syncthreads();
-    unsigned char* region = smem_raw + 256 + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
+    unsigned char* region = smem_raw + FIT_TAB_BYTES + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
     Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);

@@ -282,7 +282,7 @@ struct Pipeline {
         while (np < nmax_points) np <<= 1;
         const long long total = (long long)a.ngenes * a.nb * a.sets;
         if (total == 0) return;
-        const size_t smem_cap = 227 * 1024 - 256;   // 256 B: the CTA's 2^(j/32) table
+        const size_t smem_cap = 227 * 1024 - FIT_TAB_BYTES;
         a.np_max = np;
         a.work_counter = d_counter.p;
         a.stats = d_stats.p;
@@ -294,7 +294,7 @@ struct Pipeline {
         if (warp_team) {
             const size_t per_warp = fit_smem_per_warp(np);
             int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
-            smem = per_warp * warps + 256;
+            smem = per_warp * warps + FIT_TAB_BYTES;
             threads = warps * 32;
             grid = (int)std::min<long long>(n_sm, (total + warps - 1) / warps);
             CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -304,9 +304,9 @@ struct Pipeline {
             threads = FIT_CTA_WARPS * 32;
             grid = (int)std::min<long long>(n_sm, total);
             if (head + (size_t)np * sizeof(double) <= smem_cap) {
-                smem = head + (size_t)np * sizeof(double) + 256;
+                smem = head + (size_t)np * sizeof(double) + FIT_TAB_BYTES;
             } else {
-                smem = head + 256;
+                smem = head + FIT_TAB_BYTES;
                 const size_t need = (size_t)grid * np;
                 if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
                 a.xs_global = d_xs_scratch.p;
@@ -915,8 +915,28 @@ int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out) {
 }
 
 int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
-    static const double tab[32] = SCDD_EXP_TABLE_INIT;
-    for (int i = 0; i < n; i++) out[i] = exp_neg(x[i], tab);   // the variant the kernels are built with
+    // the kernels' softmax-term arithmetic with shift 0: out[i] = exp(x[i]).  (Inside the kernels the shift is
+    // the per-point maximum, which cancels the range-reduction constant's error; with shift 0 that error,
+    // |N| * 1.5e-19, shows up and is bounded by the test.)
+    static const double tab[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;
+    for (int i = 0; i < n; i++) {
+        const double t = term_t(x[i]);
+        out[i] = term_e(term_s(term_r(x[i], t)), term_n(x[i], t), 0, tab);
+    }
+    return SCDD_OK;
+}
+
+// softmax of G log-terms exactly as the E-step computes it (integer shift, table exp, Newton reciprocal)
+int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp) {
+    if (G < 1 || G > SCDD_GMAX) return fail(SCDD_ERR_BAD_ARG, "G out of range");
+    static const double tab[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;
+    double t[SCDD_GMAX], s[SCDD_GMAX], e[SCDD_GMAX];
+    int nn[SCDD_GMAX], M = 0;
+    for (int k = 0; k < G; k++) { t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]); M = (k == 0 || nn[k] > M) ? nn[k] : M; }
+    double S = 0.0;
+    for (int k = 0; k < G; k++) { s[k] = term_s(term_r(a[k], t[k])); e[k] = term_e(s[k], nn[k], M, tab); S += e[k]; }
+    for (int k = 0; k < G; k++) z[k] = e[k] / S;
+    if (logsumexp) *logsumexp = std::log(S) + (double)M * expc::LN2_64;
     return SCDD_OK;
 }
 

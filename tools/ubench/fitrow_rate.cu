@@ -11,9 +11,9 @@ __global__ void __launch_bounds__(512, 1) k(const double* src, int n, int np, in
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* tab = reinterpret_cast<double*>(smem_raw);
-    if (threadIdx.x < 32) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    if (threadIdx.x < SCDD_EXP_TABLE_SIZE) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
     __syncthreads();
-    unsigned char* region = smem_raw + 256 + warp * fit_smem_per_warp(np);
+    unsigned char* region = smem_raw + FIT_TAB_BYTES + warp * fit_smem_per_warp(np);
     double* pm = reinterpret_cast<double*>(region);
     Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
@@ -37,7 +37,7 @@ int main() {
     std::vector<double> h(n); for (auto& v : h) v = nd(g); std::sort(h.begin(), h.end());
     double *d, *out, *cnt; cudaMalloc(&d, n * 8); cudaMalloc(&out, 148 * 16 * 8); cudaMalloc(&cnt, 16);
     cudaMemcpy(d, h.data(), n * 8, cudaMemcpyHostToDevice);
-    size_t smem = 256 + 16 * fit_smem_per_warp(np);
+    size_t smem = FIT_TAB_BYTES + 16 * fit_smem_per_warp(np);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int gonly : {0, 2, 3, 4, 5}) {
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
