@@ -52,8 +52,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=284)                # simulateSet's default random.seed
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-genes", type=int, default=256)
-    ap.add_argument("--cpu-sample-perms", type=int, default=4)
+    ap.add_argument("--cpu-sample-genes", type=int, default=512)
+    ap.add_argument("--cpu-sample-perms", type=int, default=8)
     return ap.parse_args()
 
 
@@ -70,38 +70,48 @@ def shard_rows(ngenes, rank, world):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs (ONE long-lived nvidia-smi
+    process in loop mode: spawning a new one per sample perturbs the GPU it is measuring)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=500):
         self.idx = gpu_index
+        self.period_ms = period_ms
         self.rows = []
-        self._stop = threading.Event()
+        self._p = None
         self._t = None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    def _read(self):
+        try:
+            for line in self._p.stdout:
+                line = line.strip()
+                if line:
+                    self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                        "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._read, daemon=True)
+            self._t.start()
+        except Exception:
+            self._p = None
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
+        if self._p is not None:
+            try:
+                self._p.terminate()           # the exact process we started
+                self._p.wait(timeout=5)
+            except Exception:
+                pass
+            if self._t:
+                self._t.join(timeout=5)
         sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -111,8 +121,9 @@ class ClockSampler:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
+        pw = [float(r[3]) for r in self.rows if len(r) > 8 and r[3].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
 def cpu_baseline(args, X, cond, nthreads=0):
@@ -274,7 +285,6 @@ def main():
         T, P, fit_ms, fit_launches, rng_ms = w[0], w[1], w[2], w[3], w[4]
         # per-launch averages (summed over ranks, so divide flops and time consistently)
         alg_flops = 24.0 * T + 4.0 * P
-        achieved = alg_flops / (fit_ms * 1e-3) / 1e12 * world if fit_ms > 0 else None   # per-GPU rate x world = aggregate
         per_gpu_achieved = alg_flops / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else None
         peaks = {}
         try:

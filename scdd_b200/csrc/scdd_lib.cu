@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -51,10 +53,13 @@ struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if (p) cudaFree(p); }
+    size_t cap = 0;
+    // grows only: pipelines are cached per device, so repeated calls reuse their allocations
     void alloc(size_t count) {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (count <= cap) { n = count; return; }
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
         n = count;
-        if (count) CK(cudaMalloc((void**)&p, count * sizeof(T)));
+        if (count) { CK(cudaMalloc((void**)&p, count * sizeof(T))); cap = count; }
     }
 };
 
@@ -567,14 +572,33 @@ struct PermJob {
     std::vector<int> genes;
 };
 
+// One cached pipeline (device buffers + stream) per device: a call reuses the previous call's allocations, so the
+// end-to-end cost of scdd_perm_bf is copies + kernels, not cudaMalloc/cudaFree of gigabytes.
+struct CachedPipeline {
+    std::mutex mu;
+    std::unique_ptr<Pipeline> P;
+    cudaStream_t s = nullptr;
+};
+static CachedPipeline& cached_pipeline(int dev) {
+    static std::mutex g;
+    static std::map<int, std::unique_ptr<CachedPipeline>> m;
+    std::lock_guard<std::mutex> lk(g);
+    auto& e = m[dev];
+    if (!e) e.reset(new CachedPipeline());
+    return *e;
+}
+
 static void perm_bf_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng, int B,
                         const int32_t* perm_idx, const uint32_t* seed6, const double* cdr, const scdd_cfg* cfg,
                         double* bf_perm, uint32_t* seed6_out, scdd_stats* st) {
     if (ng == 0 || B == 0) return;
-    Pipeline P;
-    cudaStream_t s;
+    CachedPipeline& C = cached_pipeline(dev);
+    std::lock_guard<std::mutex> lk(C.mu);
     CK(cudaSetDevice(dev));
-    CK(cudaStreamCreate(&s));
+    if (!C.P) { C.P.reset(new Pipeline()); CK(cudaStreamCreate(&C.s)); }
+    Pipeline& P = *C.P;
+    P.fit_ms = P.rng_ms = P.fit_launches = 0;
+    cudaStream_t s = C.s;
     try {
         cudaEvent_t t0, t1;
         CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
@@ -629,10 +653,10 @@ static void perm_bf_one(int dev, const double* logy, const int64_t* off, const i
         st->d2h_bytes += (double)ng * B * 8.0;
         cudaEventDestroy(t0); cudaEventDestroy(t1);
     } catch (...) {
-        cudaStreamDestroy(s);
+        cudaStreamSynchronize(s);
+        cudaGetLastError();
         throw;
     }
-    CK(cudaStreamDestroy(s));
 }
 
 int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
