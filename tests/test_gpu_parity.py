@@ -259,3 +259,32 @@ def test_large_genes_permutations_and_ks():
     D, p = hp.ks(np.exp(logy), c01, off)
     oD, op = po.ks_batch(np.exp(logy), c01, off)
     assert np.array_equal(D, oD) and np.array_equal(p, op)
+
+
+def test_in_process_multi_gpu_sharding(golden_dir):
+    """scdd_set_devices: genes sharded over the visible devices inside one call (what the R shim uses);
+    must equal the single-device result bit for bit.  Skipped on a single-GPU box."""
+    if hp.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    X, cond = _load(golden_dir, "scDatEx.npz", genes=slice(0, 64))
+    logy, c01, off = hp.gene_csr(X, cond)
+    seeds = hp.gene_seeds(3, 64)
+    hp.set_devices([0])
+    one, _, s1 = hp.perm_bf(logy, c01, off, 6, seed6=seeds, cfg=hp.make_cfg(**PRIORS), return_seeds=True)
+    hp.set_devices(list(range(min(hp.device_count(), 4))))
+    many, st, s2 = hp.perm_bf(logy, c01, off, 6, seed6=seeds, cfg=hp.make_cfg(**PRIORS), return_seeds=True)
+    hp.set_devices([0])
+    assert np.array_equal(one, many) and np.array_equal(s1, s2)
+    assert st["fit_sets"] == 2 * 64 * 6
+
+
+def test_adjusted_path_larger_genes():
+    """adjust.perms = TRUE on genes of a few thousand cells (config-5 style, scaled down): oa fits by the CTA team"""
+    logy, c01, off = _big_genes([1500, 2500, 4200], seed=21)
+    rng = np.random.default_rng(4)
+    cdr = 0.3 + 0.5 * rng.random(logy.size)
+    seeds = hp.gene_seeds(8, 3)
+    out, st = hp.perm_bf(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS))
+    ref = po.perm_batch(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-6)
+    assert st["fit_sets"] == 3 * 3 * 3
