@@ -134,13 +134,13 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     if tofit.size < ngenes:
         msg(f"Notice: {ngenes - tofit.size} genes have less than {min_nonzero} nonzero cells per condition.  "
             f"Skipping these genes.")
-    # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310)
+    # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310), vectorised:
+    # length(unique(x[x > 0])) == 1  <=>  min == max over the nonzero entries
     def _const(rows):
-        out = np.zeros(rows.shape[0], dtype=bool)
-        for i, r in enumerate(rows):
-            nzv = r[r > 0]
-            out[i] = np.unique(nzv).size == 1
-        return out
+        nz = rows > 0
+        lo = np.where(nz, rows, np.inf).min(axis=1)
+        hi = np.where(nz, rows, -np.inf).max(axis=1)
+        return nz.any(axis=1) & (lo == hi)
     skip = _const(X[np.ix_(tofit, np.nonzero(isref)[0])]) | _const(X[np.ix_(tofit, np.nonzero(~isref)[0])])
     if skip.any():
         msg(f"Notice: {int(skip.sum())} Genes have constant nonzero values.  Skipping these genes.")
@@ -163,13 +163,16 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     if categorize:
         fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=cfg, with_bf=permutations != 0)
         stats["observed"] = st
-        comps_all, comps_c1, comps_c2 = np.zeros(nf), np.zeros(nf), np.zeros(nf)
-        for g in range(nf):
-            s = slice(off[g], off[g + 1])
-            c = c01[s]
-            comps_all[g] = luOutlier(cls_oa[s], min_size)
-            comps_c1[g] = luOutlier(cls_c[s][c == 0], min_size)
-            comps_c2[g] = luOutlier(cls_c[s][c == 1], min_size)
+        # luOutlier (R/Cluster_actions.R:25) for every gene at once: label counts per (gene, label)
+        gidx = np.repeat(np.arange(nf), np.diff(off))
+
+        def _lu(labels, mask):
+            cnt = np.bincount(gidx[mask] * 6 + labels[mask], minlength=nf * 6).reshape(nf, 6)
+            return (cnt[:, 1:] >= min_size).sum(axis=1).astype(np.float64)
+        allm = np.ones(gidx.size, dtype=bool)
+        comps_all = _lu(cls_oa, allm)
+        comps_c1 = _lu(cls_c, c01 == 0)
+        comps_c2 = _lu(cls_c, c01 == 1)
     if permutations == 0:
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")
