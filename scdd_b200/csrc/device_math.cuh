@@ -16,28 +16,42 @@ namespace scdd {
 // ---------------------------------------------------------------------------------------------
 // The E-step's softmax terms.  For the log-terms t_k of one point (k = 1..G) the kernels need
 // e_k = exp(t_k - shift) for ANY common shift that keeps the sum in range (log-sum-exp is shift invariant).
-//   N_k = rint(t_k * 64/ln2)                 (magic-number rounding; also the exp range reduction)
-//   M   = max_k N_k                          (integer max: the shift is M * ln2/64, the max rounded to the grid)
-//   r_k = t_k - N_k * c,  c = fl(ln2/64)     (ONE fma: the error N_k (ln2/64 - c) splits into M (..), common to all k
+//   N_k = rint(t_k * 2^TB/ln2)  (TB = 11)                 (magic-number rounding; also the exp range reduction)
+//   M   = max_k N_k                          (integer max: the shift is M ln2/2^TB, the max rounded to the grid)
+//   r_k = t_k - N_k * c,  c = fl(ln2/2^TB)   (ONE fma: the error N_k (ln2/2^TB - c) splits into M (..), common to all k
 //                                             and cancelled exactly when the log-likelihood adds the shift back as
 //                                             M * c with the same c, and (N_k - M)(..) <= 1e-16 for every term that matters)
-//   e_k = 2^((N_k - M)/64) * exp(r_k) = 2^(D >> 6) * T[D & 63] * (1 + s(r_k)),  D = N_k - M <= 0
-// s(r) = exp(r) - 1 by a degree-5 polynomial on |r| <= ln2/128 (truncation 3e-17), T = 64-entry table of 2^(j/64).
-// fp64 cost per term: 1 (t) + 1 (kf) + 1 (r) + 4 (polynomial) + 1 (s) + 1 (table fma) = 9; max, shift, table index
+//   e_k = 2^((N_k - M)/2^TB) exp(r_k) = 2^(D >> TB) * T[D & (2^TB - 1)] * (1 + s(r_k)),  D = N_k - M <= 0
+// s(r) = exp(r) - 1 by a degree-3 polynomial on |r| <= ln2/4096 (truncation 3.4e-17), T = 2048-entry table of
+// 2^(j/2048) (16 KB of shared memory per CTA).
+// fp64 cost per term: 1 (t) + 1 (kf) + 1 (r) + 2 (polynomial) + 1 (s) + 1 (table fma) = 7; max, shift, table index
 // and 2^k scaling are integer instructions.  These helpers are the single source of the arithmetic: the kernels
 // issue them column-wise over the G (or 2G) terms of a point, the host self-test calls them term by term.
 // ---------------------------------------------------------------------------------------------
-#define SCDD_EXP_TABLE_SIZE 64
-#define SCDD_EXP_TABLE_INIT {1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, 1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951}
+#define SCDD_EXP_TABLE_BITS 11
+#define SCDD_EXP_TABLE_SIZE (1 << SCDD_EXP_TABLE_BITS)
 
 namespace expc {
-constexpr double L2E64 = 92.33248261689366;            // 64 / ln 2
+constexpr int TB = SCDD_EXP_TABLE_BITS;
+constexpr int TMASK = SCDD_EXP_TABLE_SIZE - 1;
+constexpr double L2E_T = 2954.639443740597;            // 2^TB / ln 2
 constexpr double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: rint() in the low mantissa bits
-constexpr double LN2_64 = 0.010830424696249145;        // fl(ln2 / 64)
-constexpr double C2 = 0.5, C3 = 1.0 / 6.0, C4 = 1.0 / 24.0, C5 = 1.0 / 120.0;
-constexpr int NSAT = -(1 << 30);                       // N of a log-term below -2^23 ("minus infinity")
-constexpr int DMIN = -1021 * 64;                       // smallest shift kept: 2^-1021 (the reference zeroes below e^-708)
+constexpr double LN2_T = 0.00033845077175778578;       // fl(ln2 / 2^TB)
+constexpr double C2 = 0.5, C3 = 1.0 / 6.0;
+constexpr int NSAT = -(1 << 30);                       // N of a log-term below -2^19 ("minus infinity")
+constexpr int DMIN = -1021 * SCDD_EXP_TABLE_SIZE;      // smallest shift kept: 2^-1021 (the reference zeroes below e^-708)
 }  // namespace expc
+
+// 2^(j / 2^TB), j = 0 .. 2^TB - 1, correctly rounded from long double (host; uploaded to the device once)
+inline const double* exp_table_host() {
+    static double tab[SCDD_EXP_TABLE_SIZE];
+    static bool done = false;
+    if (!done) {
+        for (int j = 0; j < SCDD_EXP_TABLE_SIZE; j++) tab[j] = (double)exp2l((long double)j / (long double)SCDD_EXP_TABLE_SIZE);
+        done = true;
+    }
+    return tab;
+}
 
 SCDD_HD int hi_word(double x) {
 #if defined(__CUDA_ARCH__)
@@ -61,24 +75,22 @@ SCDD_HD double from_words(int hi, int lo) {
 #endif
 }
 
-SCDD_HD double term_t(double a) { return fma(a, expc::L2E64, expc::MAGIC); }
-// low word of t = N (two's complement) while |a| < 2^23; log-terms below -2^23 saturate
-SCDD_HD int term_n(double a, double t) { return ((unsigned)hi_word(a) >= 0xC1600000u) ? expc::NSAT : lo_word(t); }
-SCDD_HD double term_r(double a, double t) { return fma(t - expc::MAGIC, -expc::LN2_64, a); }
+SCDD_HD double term_t(double a) { return fma(a, expc::L2E_T, expc::MAGIC); }
+// low word of t = N (two's complement) while |a| < 2^19; log-terms below -2^19 saturate
+SCDD_HD int term_n(double a, double t) { return ((unsigned)hi_word(a) >= 0xC1200000u) ? expc::NSAT : lo_word(t); }
+SCDD_HD double term_r(double a, double t) { return fma(t - expc::MAGIC, -expc::LN2_T, a); }
 SCDD_HD double term_s(double r) {
     using namespace expc;
-    double p = fma(C5, r, C4);
-    p = fma(p, r, C3);
-    p = fma(p, r, C2);
+    double p = fma(C3, r, C2);
     p = fma(p, r, 1.0);
     return p * r;
 }
 SCDD_HD double term_e(double s, int n, int M, const double* tab) {
     int D = n - M;
     if (D < expc::DMIN) D = expc::DMIN;
-    const double T = tab[D & 63];
+    const double T = tab[D & expc::TMASK];
     const double v = fma(T, s, T);
-    return from_words(hi_word(v) + ((D >> 6) << 20), lo_word(v));
+    return from_words(hi_word(v) + ((D >> expc::TB) << 20), lo_word(v));
 }
 
 // ---------------------------------------------------------------------------------------------

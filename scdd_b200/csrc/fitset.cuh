@@ -160,9 +160,9 @@ __device__ __noinline__ int qclass_breaks(const double* xs, int n, int k, double
     return nbr;
 }
 
-__device__ const double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;   // source of the per-CTA shared copy
+__device__ double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE];   // source of the per-CTA shared copy, filled by init_exp_table()
 // constant-bank copies of device_math.cuh's expc:: constants (fetched with LDCU, no per-iteration immediates)
-__constant__ double EXP_TAB_CONST[6] = {92.33248261689366, -0.010830424696249145, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__constant__ double EXP_TAB_CONST[3] = {2954.639443740597, -0.00033845077175778578, 1.0 / 6.0};
 
 // 1/S for S in [1, GMAX]: MUFU.RCP64H seed + two Newton steps (5 DFMA, <= 1 ulp).  No special-case
 // branch: the argument range is known, unlike for the general-purpose __drcp_rn.
@@ -272,11 +272,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], EXP_TAB_CONST[3]);      // term_s
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], EXP_TAB_CONST[4]);
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 0.5);
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], 0.5);                   // term_s
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
@@ -438,7 +434,7 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         }
         hl += log(pl);
     }
-    hl = fma((double)hs, expc::LN2_64, hl);   // log-likelihood: sum_i log S_i + c sum_i M_i, the SAME c as in term_r
+    hl = fma((double)hs, expc::LN2_T, hl);   // log-likelihood: sum_i log S_i + c sum_i M_i, the SAME c as in term_r
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.0;
 #pragma unroll

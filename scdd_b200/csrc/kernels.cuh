@@ -284,9 +284,14 @@ __device__ __noinline__ int label_of(const Row& r, double x) {
 #define SCDD_FIT_WARPS 16
 #endif
 constexpr int FIT_MAX_WARPS = SCDD_FIT_WARPS;
+
+// uploads the 2^(j/2^TB) table to the current device (once per device per process)
+inline cudaError_t init_exp_table() {
+    return cudaMemcpyToSymbol(EXP_TABLE_GLOBAL, exp_table_host(), SCDD_EXP_TABLE_SIZE * sizeof(double));
+}
 constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
 constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
-constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/64) table    // larger fit-sets are run by a whole CTA
+constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/2048) table (16 KB)    // larger fit-sets are run by a whole CTA
 
 // per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tid = T::tid(lane);
     double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/32), shared by the CTA
-    if (threadIdx.x < SCDD_EXP_TABLE_SIZE) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) tab[i] = EXP_TABLE_GLOBAL[i];
     __syncthreads();
     unsigned char* region = smem_raw + FIT_TAB_BYTES + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned

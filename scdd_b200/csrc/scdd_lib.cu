@@ -239,6 +239,12 @@ struct Pipeline {
                 const scdd_cfg* c, const double* cdr, cudaStream_t s) {
         device = dev;
         CK(cudaSetDevice(dev));
+        {
+            static std::mutex mu;
+            static std::map<int, bool> done;
+            std::lock_guard<std::mutex> lk(mu);
+            if (!done[dev]) { CK(init_exp_table()); done[dev] = true; }
+        }
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, dev));
         n_sm = prop.multiProcessorCount;
@@ -942,7 +948,7 @@ int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
     // the kernels' softmax-term arithmetic with shift 0: out[i] = exp(x[i]).  (Inside the kernels the shift is
     // the per-point maximum, which cancels the range-reduction constant's error; with shift 0 that error,
     // |N| * 1.5e-19, shows up and is bounded by the test.)
-    static const double tab[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;
+    const double* tab = exp_table_host();
     for (int i = 0; i < n; i++) {
         const double t = term_t(x[i]);
         out[i] = term_e(term_s(term_r(x[i], t)), term_n(x[i], t), 0, tab);
@@ -953,14 +959,14 @@ int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
 // softmax of G log-terms exactly as the E-step computes it (integer shift, table exp, Newton reciprocal)
 int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp) {
     if (G < 1 || G > SCDD_GMAX) return fail(SCDD_ERR_BAD_ARG, "G out of range");
-    static const double tab[SCDD_EXP_TABLE_SIZE] = SCDD_EXP_TABLE_INIT;
+    const double* tab = exp_table_host();
     double t[SCDD_GMAX], s[SCDD_GMAX], e[SCDD_GMAX];
     int nn[SCDD_GMAX], M = 0;
     for (int k = 0; k < G; k++) { t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]); M = (k == 0 || nn[k] > M) ? nn[k] : M; }
     double S = 0.0;
     for (int k = 0; k < G; k++) { s[k] = term_s(term_r(a[k], t[k])); e[k] = term_e(s[k], nn[k], M, tab); S += e[k]; }
     for (int k = 0; k < G; k++) z[k] = e[k] / S;
-    if (logsumexp) *logsumexp = std::log(S) + (double)M * expc::LN2_64;
+    if (logsumexp) *logsumexp = std::log(S) + (double)M * expc::LN2_T;
     return SCDD_OK;
 }
 

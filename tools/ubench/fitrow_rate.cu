@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(512, 1) k(const double* src, int n, int np, in
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* tab = reinterpret_cast<double*>(smem_raw);
-    if (threadIdx.x < SCDD_EXP_TABLE_SIZE) tab[threadIdx.x] = EXP_TABLE_GLOBAL[threadIdx.x];
+    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) tab[i] = EXP_TABLE_GLOBAL[i];
     __syncthreads();
     unsigned char* region = smem_raw + FIT_TAB_BYTES + warp * fit_smem_per_warp(np);
     double* pm = reinterpret_cast<double*>(region);
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(512, 1) k(const double* src, int n, int np, in
     if (lane == 0) { atomicAdd(&counters[0], st->triples); atomicAdd(&counters[1], st->em_iters); out[blockIdx.x * 16 + warp] = rows[4].bic; }
 }
 int main() {
+    init_exp_table();
     int n = 880, np = 1024;
     std::mt19937 g(1); std::normal_distribution<double> nd(3.0, 1.0);
     std::vector<double> h(n); for (auto& v : h) v = nd(g); std::sort(h.begin(), h.end());
