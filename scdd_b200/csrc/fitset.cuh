@@ -240,7 +240,9 @@ __device__ __forceinline__ int tree_imax(const int* v) {
 // every step is emitted for all U*G terms before the next one, so the in-order warp always has U*G independent
 // fp64 instructions between an operation and its consumer (ptxas -O2/-O3 would re-serialise the chains).
 //   Outputs: e (U*G), d = x - mu, q = d^2, S = sum_k e_k and the integer shift M per point.
-template <int G, int U, class P>
+// SAT = false drops the saturation test of term_n: legal when the caller has proved |t_k| < 2^19 for every point
+// (all variances above (data range)^2 / 2^20 -- see fit_row), which is the case for all but degenerate fits.
+template <int G, int U, bool SAT, class P>
 __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
                                              double (&q)[U * G], double (&S)[U], int (&M)[U]) {
     using namespace expc;
@@ -264,7 +266,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);                 // term_t
 #pragma unroll
-    for (int i = 0; i < N; i++) n[i] = term_n(a[i], t[i]);
+    for (int i = 0; i < N; i++) n[i] = SAT ? term_n(a[i], t[i]) : __double2loint(t[i]);
 #pragma unroll
     for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&n[u * G]);
 #pragma unroll
@@ -280,7 +282,15 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int k = 0; k < G; k++) e[u * G + k] = term_e(p[u * G + k], n[u * G + k], M[u], prm.tab);
+        for (int k = 0; k < G; k++) {                                                      // term_e
+            const int i = u * G + k;
+            const int D = max(n[i] - M[u], DMIN);
+            const double T = prm.tab[D & TMASK];
+            const double v = fma(T, p[i], T);
+            int hi;   // hi(v) + ((D >> TB) << 20) as shift + multiply-add (two integer instructions, not three)
+            asm("{ .reg .s32 k; shr.s32 k, %1, %2; mad.lo.s32 %0, k, 1048576, %3; }" : "=r"(hi) : "r"(D), "n"(TB), "r"(__double2hiint(v)));
+            e[i] = __hiloint2double(hi, __double2loint(v));
+        }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) S[u] = tree_sum<G>(&e[u * G]);
@@ -292,7 +302,7 @@ __device__ __forceinline__ int map_label(double x, const P& prm) {
     double xx[1] = {x};
     double e[G], d[G], q[G], S[1];
     int M[1];
-    estep_points<G, 1, P>(xx, prm, e, d, q, S, M);
+    estep_points<G, 1, true, P>(xx, prm, e, d, q, S, M);
     double rs = rcp_sum(S[0]);
     double best = __dmul_rn(e[0], rs);
     int bk = 0;
@@ -361,12 +371,12 @@ struct Team {
 //   mu = mu_old + S(z d)/S(z),  sigsq = S(z q)/S(z) - (S(z d)/S(z))^2
 // which equals mclust's two-pass update in exact arithmetic and needs no stored z matrix.
 // ---------------------------------------------------------------------------------------------
-template <int G, int U, class P>
+template <int G, int U, bool SAT, class P>
 __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
                                                   double (&C)[G], double& pl, long long& hs) {
     double e[U * G], d[U * G], q[U * G], S[U];
     int M[U];
-    estep_points<G, U, P>(x, prm, e, d, q, S, M);
+    estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M);
 #pragma unroll
     for (int u = 0; u < U; u++) {
         double rs = rcp_sum(S[u]);
@@ -386,13 +396,24 @@ __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P&
 #define SCDD_PARAMS_SMEM 1
 #endif
 
+#ifndef SCDD_PARAMS_REG_MAXG
+#define SCDD_PARAMS_REG_MAXG 3      // G <= 3: 6G registers are affordable and save 2 shared loads per term
+#endif
 template <int G>
 __device__ __forceinline__ auto load_params(const double* pm, const double* tab) {
 #if SCDD_PARAMS_SMEM
-    ParamsSmem p;
-    p.tab = tab;
-    p.addr = (unsigned)__cvta_generic_to_shared(pm);
-    return p;
+    if constexpr (G > SCDD_PARAMS_REG_MAXG) {
+        ParamsSmem p;
+        p.tab = tab;
+        p.addr = (unsigned)__cvta_generic_to_shared(pm);
+        return p;
+    } else {
+        ParamsReg<G> p;
+        p.tab = tab;
+#pragma unroll
+        for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
+        return p;
+    }
 #else
     ParamsReg<G> p;
     p.tab = tab;
@@ -402,7 +423,7 @@ __device__ __forceinline__ auto load_params(const double* pm, const double* tab)
 #endif
 }
 
-template <int G, int U, int TW>
+template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            const double* tab, double (&v)[16]) {
     constexpr int NT = Team<TW>::NT;
@@ -423,13 +444,13 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
             double x[U];
 #pragma unroll
             for (int u = 0; u < U; u++) x[u] = xs[i + NT * u];
-            accumulate_points<G, U>(x, prm, A, B, C, pl, hs);
+            accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hs);
         }
         if (U > 1) {
 #pragma unroll 1
             for (; i < stop; i += NT) {
                 double x[1] = {xs[i]};
-                accumulate_points<G, 1>(x, prm, A, B, C, pl, hs);
+                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hs);
             }
         }
         hl += log(pl);
@@ -477,10 +498,24 @@ __device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, in
                                               const double* tab, double* red) {
     double v[16];
     switch (G) {
-        case 2: estep_pass<2, Unroll<2>::value, TW>(xs, n, lane, pm, tab, v); break;
-        case 3: estep_pass<3, Unroll<3>::value, TW>(xs, n, lane, pm, tab, v); break;
-        case 4: estep_pass<4, Unroll<4>::value, TW>(xs, n, lane, pm, tab, v); break;
-        default: estep_pass<5, Unroll<5>::value, TW>(xs, n, lane, pm, tab, v); break;
+        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, tab, v); break;
+        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, tab, v); break;
+        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, tab, v); break;
+        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, tab, v); break;
+    }
+    return Team<TW>::reduce(v, lane, red);
+}
+
+// same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code
+template <int TW>
+__device__ __noinline__ double estep_dispatch_sat(int G, const double* xs, int n, int lane, const double* pm,
+                                                  const double* tab, double* red) {
+    double v[16];
+    switch (G) {
+        case 2: estep_pass<2, 1, TW, true>(xs, n, lane, pm, tab, v); break;
+        case 3: estep_pass<3, 1, TW, true>(xs, n, lane, pm, tab, v); break;
+        case 4: estep_pass<4, 1, TW, true>(xs, n, lane, pm, tab, v); break;
+        default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, tab, v); break;
     }
     return Team<TW>::reduce(v, lane, red);
 }
@@ -516,6 +551,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
     if (G > n) return;   // mclustBIC: G <- G[G <= n]
     const int kown = lane < G ? lane : 0;
     const bool owner = lane < G;
+    const double range2 = (xs[n - 1] - xs[0]) * (xs[n - 1] - xs[0]);   // xs is sorted: every |x - mu_k| <= range
 
     double br[GMAX];
     const int nbr = qclass_breaks(xs, n, G, br);
@@ -576,7 +612,11 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         T::sync();
         if (owner && T::lead()) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
         T::sync();
-        const double t = estep_dispatch<TW>(G, xs, n, lane, pm, tab, red);
+        // |t_k| <= |lc_k| + range^2 / (2 sigsq_k) with |lc_k| < 100: below 2^19 for every point iff the smallest
+        // variance exceeds range^2 / 2^20; then the integer extraction needs no saturation test (fast pass)
+        const bool wide = !__any_sync(FULLMASK, owner && !(sig_own * 1.0e6 > range2));
+        const double t = wide ? estep_dispatch<TW>(G, xs, n, lane, pm, tab, red)
+                              : estep_dispatch_sat<TW>(G, xs, n, lane, pm, tab, red);
         A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
         hood = slot(t, 3 * G);
         // stop when |hold - hood| / (1 + |hood|) <= tol  (tested in product form: no division on the critical path)
