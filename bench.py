@@ -153,7 +153,7 @@ def run_reference(args):
     from oracle import pyoracle as po
     from scdd_b200 import hotpath as hp
     X, cond = workload(args)
-    ng = min(128, X.shape[0])
+    ng = min(512, X.shape[0])        # enough genes to keep every host thread busy (OpenMP over genes)
     rows = np.linspace(0, X.shape[0] - 1, ng).astype(int)
     logy, c01, off = hp.gene_csr(X[rows], cond)
     seeds = hp.gene_seeds(args.seed, ng)
