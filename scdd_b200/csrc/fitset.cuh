@@ -8,10 +8,10 @@
 // (the fits are deterministic in y), so the warp computes the five rows once and then runs the
 // reference's scalar decision procedure on them.
 //
-// Data placement: the vector lives in the warp's shared-memory slab, SORTED (the EM sums and the
-// selection are order independent; sorting makes mclust's quantile initialisation a lookup).
-// Lanes own points i = lane, lane+32, ...; sufficient statistics are reduced with warp shuffles.
-// All arithmetic is fp64.
+// Data placement: the vector lives in the team's slab (a warp's shared-memory slab, or for large vectors a
+// CTA's shared / L2-resident slab), SORTED (the EM sums and the selection are order independent; sorting makes
+// mclust's quantile initialisation a lookup).  Threads own points i = tid, tid + team size, ...; sufficient
+// statistics are reduced with warp shuffles (plus one shared-memory hop for CTA teams).  All arithmetic is fp64.
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -50,33 +50,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
     return v;
-}
-
-template <int NV>
-__device__ __forceinline__ void warp_sum_vec(double (&v)[NV]) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int j = 0; j < NV; j++) v[j] += __shfl_xor_sync(FULLMASK, v[j], o);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// in-place ascending bitonic sort of np (power of two) doubles in shared memory by one warp
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_sort(double* xs, int np, int lane) {
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (np >> 1); t += 32) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool up = ((i & k) == 0);
-                double a = xs[i], b = xs[l];
-                if ((a > b) == up) { xs[i] = b; xs[l] = a; }
-            }
-            __syncwarp();
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +137,7 @@ __device__ double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE];   // source of the per-
 // constant-bank copies of device_math.cuh's expc:: constants (fetched with LDCU, no per-iteration immediates)
 __constant__ double EXP_TAB_CONST[3] = {2954.639443740597, -0.00033845077175778578, 1.0 / 6.0};
 
-// 1/S for S in [1, GMAX]: MUFU.RCP64H seed + two Newton steps (5 DFMA, <= 1 ulp).  No special-case
+// 1/S for S in (0.97, 1.03 GMAX]: MUFU.RCP64H seed + one cubic Newton step (3 DFMA, ~1 ulp).  No special-case
 // branch: the argument range is known, unlike for the general-purpose __drcp_rn.
 __device__ __forceinline__ double rcp_sum(double x) {
 #ifndef SCDD_FAST_RCP
@@ -197,16 +170,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // Component parameters in E-step form: mu_k, nh_k = -1/(2 sigsq_k), lc_k = log pro_k - (log 2 pi + log sigsq_k)/2.
 // ParamsReg keeps them in registers (3G doubles per lane); ParamsSmem re-reads them from the warp's
-// shared-memory block for every point (broadcast loads on the LSU pipe), which frees 6G registers for
-// the interleaved exp() chains -- the fp64 pipe, not the LSU, is the bottleneck of this kernel.
+// shared-memory block for every point (broadcast loads on the LSU pipe), which frees 6G registers; used for
+// G >= 4, where the register file is the scarcer resource (load_params).
 template <int G>
 struct ParamsReg {
-    const double* tab;   // 2^(j/32) table
+    const double* tab;   // 2^(j/2048) table
     double mu[G], nh[G], lc[G];
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
-    const double* tab;   // 2^(j/64) table (shared memory)
+    const double* tab;   // 2^(j/2048) table (shared memory)
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
@@ -214,8 +187,6 @@ struct ParamsSmem {
     }
 };
 
-// U points x G components: unnormalised responsibilities e = exp(t - max t), d = x - mu, q = d^2,
-// per point S = sum_k e and the max.
 // sum of G values as a balanced tree (dependency depth ceil(log2 G) instead of G - 1)
 template <int G>
 __device__ __forceinline__ double tree_sum(const double* e) {
@@ -236,9 +207,9 @@ __device__ __forceinline__ int tree_imax(const int* v) {
     return m;
 }
 
-// U points x G components: softmax terms (device_math.cuh, "The E-step's softmax terms"), issued column-wise:
-// every step is emitted for all U*G terms before the next one, so the in-order warp always has U*G independent
-// fp64 instructions between an operation and its consumer (ptxas -O2/-O3 would re-serialise the chains).
+// U points x G components: softmax terms (device_math.cuh, "The E-step's softmax terms"), written column-wise:
+// every step is emitted for all U*G terms before the next one (U*G independent fp64 instructions between an
+// operation and its consumer; ptxas is free to re-order, see DESIGN.md "Issue model").
 //   Outputs: e (U*G), d = x - mu, q = d^2, S = sum_k e_k and the integer shift M per point.
 // SAT = false drops the saturation test of term_n: legal when the caller has proved |t_k| < 2^19 for every point
 // (all variances above (data range)^2 / 2^20 -- see fit_row), which is the case for all but degenerate fits.

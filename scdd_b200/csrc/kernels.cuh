@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tid = T::tid(lane);
-    double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/32), shared by the CTA
+    double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/2048), shared by the CTA
     for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) tab[i] = EXP_TABLE_GLOBAL[i];
     __syncthreads();
     unsigned char* region = smem_raw + FIT_TAB_BYTES + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
