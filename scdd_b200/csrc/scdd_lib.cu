@@ -245,9 +245,7 @@ struct Pipeline {
             std::lock_guard<std::mutex> lk(mu);
             if (!done[dev]) { CK(init_exp_table()); done[dev] = true; }
         }
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, dev));
-        n_sm = prop.multiProcessorCount;
+        if (n_sm == 0) CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         ngenes = ng;
         cfg = to_dev(c);
         h_off.assign(gene_off, gene_off + ng + 1);
