@@ -74,6 +74,7 @@ typedef struct {
     double rng_kernel_ms;  /* device time of the permutation-generation kernel(s) */
     double total_ms;       /* device time of the whole call, first H2D to last D2H */
     double h2d_bytes, d2h_bytes;
+    double debug_violations; /* index/bounds checks that failed; only counted in -DSCDD_DEBUG_BOUNDS builds (else 0) */
 } scdd_stats;
 
 /* ---- library / device management ---- */

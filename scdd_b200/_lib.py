@@ -39,7 +39,7 @@ class Fit(C.Structure):
 
 STATS_FIELDS = ["triples", "point_iters", "fit_sets", "em_iters", "iter_cap_hits", "tol_near", "bic_near",
                 "const_sets", "failed_sets", "fit_kernel_ms", "fit_kernel_launches", "rng_kernel_ms", "total_ms",
-                "h2d_bytes", "d2h_bytes"]
+                "h2d_bytes", "d2h_bytes", "debug_violations"]
 
 
 class Stats(C.Structure):

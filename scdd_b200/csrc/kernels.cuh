@@ -241,6 +241,14 @@ __global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes,
 // ------------------------------------------------------------------------------------------------
 enum PermKind { PERM_NONE = 0, PERM_I32_1BASED = 1, PERM_U16 = 2, PERM_U32 = 3 };
 
+// compute-sanitizer is closed on the build pool, so index checks are compiled in on demand
+// (-DSCDD_DEBUG_BOUNDS): a failed check bumps stats[9] and the tests assert it stays 0.
+#ifdef SCDD_DEBUG_BOUNDS
+#define SCDD_CHECK(stats, cond) do { if (!(cond)) atomicAdd(&(stats)[9], 1.0); } while (0)
+#else
+#define SCDD_CHECK(stats, cond) do { } while (0)
+#endif
+
 struct FitArgs {
     const double* vals;        // logy, or lm residuals on the adjusted path
     const double* fitted;      // nullptr, or lm fitted values (adjusted path): x = log(exp(fitted + resid[perm]))
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             if (j < n) {
                 uint32_t i = a.part[o + pofs + j];
                 uint32_t src = perm_lookup(a, o, ng, b, i);
+                SCDD_CHECK(a.stats, i < (uint32_t)ng && src < (uint32_t)ng && np <= a.np_max);
                 v = a.vals[o + src];
                 if (a.fitted) v = log(exp(a.fitted[o + i] + v));   // R/permutations.R:244,251-252
             }

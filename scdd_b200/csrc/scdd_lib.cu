@@ -421,6 +421,7 @@ struct Pipeline {
         st->triples += h[0]; st->point_iters += h[1]; st->em_iters += h[2]; st->iter_cap_hits += h[3];
         st->tol_near += h[4]; st->bic_near += h[5]; st->const_sets += h[6]; st->failed_sets += h[7];
         st->fit_sets += h[8];
+        st->debug_violations += h[9];
         st->fit_kernel_ms += fit_ms; st->rng_kernel_ms += rng_ms; st->fit_kernel_launches += fit_launches;
     }
 };

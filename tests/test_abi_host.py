@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Cfg) == 5 * 8 + 4 * 4
     assert C.sizeof(_lib.Fit) == 4 * 4 + 2 * 8 + 2 * 5 * 8 == _lib.FIT_DTYPE.itemsize
-    assert C.sizeof(_lib.Stats) == 15 * 8
+    assert C.sizeof(_lib.Stats) == 16 * 8
 
 
 def test_compute_fails_loudly_without_gpu():

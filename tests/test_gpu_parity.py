@@ -288,3 +288,14 @@ def test_adjusted_path_larger_genes():
     ref = po.perm_batch(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
     np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-6)
     assert st["fit_sets"] == 3 * 3 * 3
+
+
+def test_debug_bounds_build_reports_no_violation(golden_dir):
+    """when run against a -DSCDD_DEBUG_BOUNDS build (SCDD_LIB_OVERRIDE), every gather index was in range;
+    with the release build the counter is simply 0"""
+    X, cond = _load(golden_dir, "scDatEx.npz", genes=slice(0, 100))
+    logy, c01, off = hp.gene_csr(X, cond)
+    out, st = hp.perm_bf(logy, c01, off, 8, seed6=hp.gene_seeds(1, 100), cfg=hp.make_cfg(**PRIORS))
+    assert st["debug_violations"] == 0
+    _, _, _, _, _, st2 = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
+    assert st2["debug_violations"] == 0

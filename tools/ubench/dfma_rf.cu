@@ -12,6 +12,11 @@ __global__ void k(double* out, int iters, double seed) {
         if (MODE == 0) {
 #pragma unroll
             for (int j = 0; j < 8; j++) a[j] = fma(a[j], 0.999999, 1e-9);                 // immediates / uniform operands
+        } else if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = fma(b[j], a[j], 1e-9);                      // two distinct registers + immediate
+#pragma unroll
+            for (int j = 0; j < 8; j++) { double t = b[j]; b[j] = c[j]; c[j] = t; }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) a[j] = fma(b[j], c[j], a[j]);                      // three distinct registers
@@ -41,5 +46,6 @@ int main() {
     run<0, 0>(sms, d, "DFMA reg,imm,imm"); run<1, 0>(sms, d, "DFMA reg,reg,reg");
     run<1, 4>(sms, d, "DFMA reg,reg,reg"); run<1, 8>(sms, d, "DFMA reg,reg,reg"); run<1, 12>(sms, d, "DFMA reg,reg,reg");
     run<0, 8>(sms, d, "DFMA reg,imm,imm");
+    run<2, 0>(sms, d, "DFMA reg,reg,imm"); run<2, 4>(sms, d, "DFMA reg,reg,imm"); run<2, 8>(sms, d, "DFMA reg,reg,imm");
     return 0;
 }
