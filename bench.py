@@ -243,10 +243,15 @@ def main():
     work = torch.tensor([d["triples"], d["point_iters"], d["fit_kernel_ms"], d["fit_kernel_launches"], d["rng_kernel_ms"],
                          d["fit_sets"], d["tol_near"], d["bic_near"], d["failed_sets"], d["iter_cap_hits"]],
                         dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device="cuda")     # diagnostics: step ms, fit ms, SM MHz per rank
+    per_rank[rank, 0] = ms / args.steps
+    per_rank[rank, 1] = d["fit_kernel_ms"] / max(1.0, d["fit_kernel_launches"])
+    per_rank[rank, 2] = clocks["sm_mhz"] or 0.0
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
     total_units = float(units.item())
     value = total_units / (ms_max * 1e-3)
@@ -315,6 +320,9 @@ def main():
                        "l2": "per-step inputs (gene values + permutation indices, >0.6 GB) exceed the 126 MB L2",
                        "priors": PRIORS},
             "clocks": clocks,
+            "per_rank": {"ms_per_step": [round(v, 2) for v in per_rank[:, 0].tolist()],
+                         "fit_kernel_ms": [round(v, 2) for v in per_rank[:, 1].tolist()],
+                         "sm_mhz": per_rank[:, 2].tolist()},
             "e2e": e2e,
             "gpu_launches": int(3 * args.steps * world),
             "roofline": {"bound": "fp64", "achieved": per_gpu_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
