@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genes", type=int, default=20000)
     ap.add_argument("--cells", type=int, default=2000)
-    ap.add_argument("--perms-per-step", type=int, default=8)
+    ap.add_argument("--perms-per-step", type=int, default=16)
     ap.add_argument("--seed", type=int, default=284)                # simulateSet's default random.seed
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
