@@ -262,6 +262,8 @@ struct FitArgs {
     int ngenes, nb, sets;      // sets per (gene, permutation): 2 = (c1, c2), 3 = (c1, c2, oa)
     int np_max;                // slab capacity (power of two)
     double* xs_global;         // CTA teams only: per-CTA slabs in global memory when np_max exceeds shared memory
+    const int32_t* gene_order; // nullable: genes in decreasing expected cost (longest-processing-time-first)
+    double* gene_cost;         // nullable: [ngenes] accumulated EM work (triples) per gene, feeds gene_order
     double* jp;                // [ngenes * nb * sets] log joint posterior of each fit-set
     scdd_fit* fits;            // observed-data detail outputs (nullable): [3 * ngenes] as (oa, c1, c2)
     int32_t* cls_oa;
@@ -349,8 +351,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
         const int w = (int)(item % a.sets);
         const long long u = item / a.sets;
         const int b = (int)(u % a.nb);
-        const int g = (int)(u / a.nb);
+        const int g = a.gene_order ? a.gene_order[(int)(u / a.nb)] : (int)(u / a.nb);
         const int64_t o = a.gene_off[g];
+        const double work0 = st->triples;
         const int ng = (int)(a.gene_off[g + 1] - o);
         const int n1 = a.n1[g];
         int n, pofs;
@@ -385,7 +388,10 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, tab, red);
             if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
         }
-        if (lead0) a.jp[item] = jp;
+        if (lead0) {
+            a.jp[((long long)g * a.nb + b) * a.sets + w] = jp;
+            if (a.gene_cost) atomicAdd(&a.gene_cost[g], st->triples - work0);
+        }
 
         // ---- observed-data detail: the list mclustRestricted returns ----
         if (a.fits) {

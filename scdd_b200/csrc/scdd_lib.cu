@@ -200,6 +200,10 @@ struct Pipeline {
     DevBuf<uint32_t> d_part, d_seeds;
     DevBuf<unsigned long long> d_counter;
     DevBuf<unsigned char> d_perm, d_scratch;
+    DevBuf<double> d_gene_cost;      // EM work per gene measured on the first chunk ...
+    DevBuf<int32_t> d_gene_order;    // ... and the resulting longest-first gene order used by later chunks
+    bool have_order = false;
+    uint64_t layout_hash = 0;
     std::vector<int64_t> h_off;
     bool adjusted = false;
     bool wide_idx = false;   // permutation indices need 32 bits
@@ -252,6 +256,12 @@ struct Pipeline {
         const int64_t base = h_off[0];
         for (auto& v : h_off) v -= base;
         nnz = (size_t)h_off[ng];
+        {   // the cost order survives a re-upload of the same gene layout (repeated calls on one data set)
+            uint64_t h = 1469598103934665603ULL;
+            for (auto v : h_off) { h ^= (uint64_t)v; h *= 1099511628211ULL; }
+            if (h != layout_hash) have_order = false;
+            layout_hash = h;
+        }
         max_n = 0;
         for (int g = 0; g < ng; g++) max_n = std::max<int>(max_n, (int)(h_off[g + 1] - h_off[g]));
         d_logy.alloc(nnz); d_off.alloc(ng + 1); d_cond.alloc(nnz); d_part.alloc(nnz); d_n1.alloc(ng);
@@ -351,7 +361,29 @@ struct Pipeline {
         a.part = d_part.p;
         a.n1 = d_n1.p;
         a.ngenes = ngenes;
+        a.gene_order = have_order ? d_gene_order.p : nullptr;
+        a.gene_cost = nullptr;
         return a;
+    }
+
+    // Longest-processing-time-first scheduling of the persistent fit kernel.  The EM work of a gene's permuted
+    // fit-sets is a property of the gene's pooled distribution, so the work measured on one chunk predicts the
+    // next: genes are then started in decreasing cost order and the kernel's tail consists of cheap fit-sets.
+    void begin_cost_measurement(cudaStream_t s) {
+        d_gene_cost.alloc(ngenes);
+        CK(cudaMemsetAsync(d_gene_cost.p, 0, (size_t)ngenes * sizeof(double), s));
+    }
+    void finish_cost_measurement(cudaStream_t s) {
+        std::vector<double> cost(ngenes);
+        CK(cudaMemcpyAsync(cost.data(), d_gene_cost.p, (size_t)ngenes * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<int32_t> order(ngenes);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cost[x] > cost[y]; });
+        d_gene_order.alloc(ngenes);
+        CK(cudaMemcpyAsync(d_gene_order.p, order.data(), (size_t)ngenes * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        have_order = true;
     }
 
     // device buffers for `bc` permutations per gene drawn on the device
@@ -407,7 +439,10 @@ struct Pipeline {
         a.nb = nb;
         a.sets = adjusted ? 3 : 2;
         a.jp = d_jp.p;
+        const bool measure = !have_order && ngenes >= 2 * n_sm;   // worth ordering only when genes outnumber the SMs
+        if (measure) { begin_cost_measurement(s); a.gene_cost = d_gene_cost.p; }
         launch_fit(s, a, adjusted ? max_n : max_half);
+        if (measure) finish_cost_measurement(s);
         const long long units = (long long)ngenes * nb;
         combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(d_jp.p, ngenes, nb, a.sets, bf_out, ld, col0);
         CK(cudaGetLastError());
