@@ -299,3 +299,35 @@ def test_debug_bounds_build_reports_no_violation(golden_dir):
     assert st["debug_violations"] == 0
     _, _, _, _, _, st2 = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS))
     assert st2["debug_violations"] == 0
+
+
+def test_edge_cases_empty_and_degenerate_inputs():
+    """empty gene lists, B = 0, a gene whose cells all belong to one condition, constant values"""
+    cfg = hp.make_cfg(**PRIORS)
+    e = np.zeros(0)
+    off0 = np.zeros(1, dtype=np.int64)
+    fits, coa, cc, bf, den, st = hp.fit_observed(e, e.astype(np.int32), off0, cfg=cfg)
+    assert fits.shape == (0, 3) and bf.size == 0
+    out, _ = hp.perm_bf(e, e.astype(np.int32), off0, 5, seed6=np.zeros((0, 6), dtype=np.uint32), cfg=cfg)
+    assert out.shape == (0, 5)
+    D, p = hp.ks(e, e.astype(np.int32), off0)
+    assert D.size == 0
+    rng = np.random.default_rng(0)
+    y = rng.normal(3, 1, 40)
+    c = (np.arange(40) % 2).astype(np.int32)
+    off = np.array([0, 40], dtype=np.int64)
+    out, _ = hp.perm_bf(y, c, off, 0, seed6=hp.gene_seeds(1, 1), cfg=cfg)
+    assert out.shape == (1, 0)
+    # one condition empty: the c2 fit-set has no points -> reported, NaN, never silently fitted
+    with pytest.raises(hp.ScddError) as ei:
+        hp.perm_bf(y, np.zeros(40, dtype=np.int32), off, 2, seed6=hp.gene_seeds(1, 1), cfg=cfg)
+    assert ei.value.code == -5
+    out, st = hp.perm_bf(y, np.zeros(40, dtype=np.int32), off, 2, seed6=hp.gene_seeds(1, 1), cfg=cfg, allow_failed=True)
+    assert np.isnan(out).all() and st["failed_sets"] == 2
+    D, p = hp.ks(np.exp(y), np.zeros(40, dtype=np.int32), off)
+    assert np.isnan(D[0]) and np.isnan(p[0])          # ks.test: "not enough 'y' data"
+    # all-identical values in one condition: the reference would jitter with runif (R/mclust.restricted.R:48-50)
+    yc = y.copy()
+    yc[c == 1] = 2.5
+    fits, coa, cc, bf, den, st = hp.fit_observed(yc, c, off, cfg=cfg, allow_failed=True)
+    assert st["const_sets"] == 1 and fits[0, 2]["G"] == 0 and fits[0, 0]["G"] >= 1 and np.isnan(bf[0])
