@@ -193,13 +193,12 @@ __global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes,
                 }
                 if (lane == 0) {
                     // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
-                    const uint64_t one = 1;
-                    uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
-                    while (i < n && used < PG_BLOCK) {
-                        vacc = 65536ULL * vacc + (uint64_t)cand[used++];
-                        if (--need == 0) {
-                            uint64_t v = vacc & mask;
-                            if (v < (uint64_t)m) {
+                    if (n <= 32768u) {
+                        // ceil(log2 m) <= 15: one 16-bit chunk per attempt, everything fits 32-bit arithmetic
+                        uint32_t mask = (1u << bits) - 1u;
+                        while (i < n && used < PG_BLOCK) {
+                            const uint32_t v = (uint32_t)cand[used++] & mask;
+                            if (v < m) {
                                 // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the
                                 // active range receives y[i]: the array ends up holding the permutation reversed.
                                 const IdxT pick = arr[v];
@@ -209,11 +208,31 @@ __global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes,
                                 i++;
                                 if ((m & (m - 1)) == 0) {   // ceil(log2 m) changes only at powers of two
                                     bits = index_bits(m);
-                                    mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                    mask = (1u << bits) - 1u;
                                 }
                             }
-                            vacc = 0;
-                            need = bits / 16 + 1;
+                        }
+                    } else {
+                        const uint64_t one = 1;
+                        uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                        while (i < n && used < PG_BLOCK) {
+                            vacc = 65536ULL * vacc + (uint64_t)cand[used++];
+                            if (--need == 0) {
+                                uint64_t v = vacc & mask;
+                                if (v < (uint64_t)m) {
+                                    const IdxT pick = arr[v];
+                                    --m;
+                                    arr[v] = arr[m];
+                                    arr[m] = pick;
+                                    i++;
+                                    if ((m & (m - 1)) == 0) {
+                                        bits = index_bits(m);
+                                        mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                    }
+                                }
+                                vacc = 0;
+                                need = bits / 16 + 1;
+                            }
                         }
                     }
                 }
