@@ -125,6 +125,34 @@ int32_t scdd_rng_sample_perms(uint32_t* state6, int32_t n, int32_t B, int32_t* o
 /* Mersenne-Twister path: set.seed(seed); then `count` calls of sample(1:n); out [count*n] */
 int32_t scdd_rng_mt_sample_perms(uint32_t seed, int32_t n, int32_t count, int32_t* out);
 
+/* ---- dense genes x cells matrix <-> the layout above (host, multi-threaded marshalling; no GPU needed) ----
+ * X: normalized counts, ngenes x ncells; col_major = 1 for an R matrix (X[g + c*ngenes]), 0 for C order.
+ * cell_cond01[ncells]: 0 = reference condition.  These replace the apply()/for loops over genes that surround
+ * the hot path in scDD().
+ *
+ * scdd_dense_scan: the per-gene filters -- nnz0/nnz1 = nonzero cells per condition (tofit, R/scDD.R:270-274),
+ * const0/const1 = 1 when all nonzero values of that condition are identical (skipConstant, R/scDD.R:292-298),
+ * n_negative = sum(X < 0) (R/scDD.R:262).  Any output may be NULL. */
+int32_t scdd_dense_scan(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                        int32_t* nnz0, int32_t* nnz1, uint8_t* const0, uint8_t* const1, int64_t* n_negative);
+/* scdd_dense_to_csr: gathers rows genes[nsel] (0-based; NULL = rows 0..nsel-1) into (vals, cond01).
+ * gene_off[nsel+1] is INPUT: prefix sums of nnz0+nnz1 (of ncells when incl_zero).  vals = log(x) when take_log
+ * (`y <- log(y[y>0])`, R/scDD.R:374-375; libm log, as R calls), zeros kept only when incl_zero (R/Test_KS.R:57-64). */
+int32_t scdd_dense_to_csr(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                          const int32_t* genes, int32_t nsel, int32_t take_log, int32_t incl_zero,
+                          const int64_t* gene_off, double* vals, int32_t* cond01);
+/* scdd_labels_to_dense: the Zhat matrices, R/scDD.R:528-552.  Z (same layout as X) = 0 where X == 0, the class
+ * label on the nonzero cells of the selected genes (labels in CSR order over ALL their nonzero cells), 1 elsewhere.
+ * which = -1: all cells (Zhat.combined); 0 / 1: only that condition's cells (Zhat.c1 / Zhat.c2 -- Z then has
+ * that many columns). */
+int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                             int32_t which, const int32_t* genes, int32_t nsel, const int64_t* gene_off,
+                             const int32_t* labels, double* Z);
+/* scdd_cluster_counts: luOutlier, R/Cluster_actions.R:25 -- per gene sum(table(class) >= min_size), over all its
+ * cells (which = -1, comps.all) or those of one condition (which = 0 / 1, comps.c1 / comps.c2). */
+int32_t scdd_cluster_counts(const int32_t* labels, const int32_t* cond01, const int64_t* gene_off, int32_t ngenes,
+                            int32_t min_size, int32_t which, int32_t* counts);
+
 /* ---- device-resident plan (throughput harness; inputs stay in HBM between steps) ---- */
 typedef struct scdd_plan scdd_plan;
 /* uploads the gene block to `device`, runs the per-gene preparation kernels.

@@ -4,14 +4,23 @@
 # Genes table) stays the reference's own R code.  NAMESPACE gains  useDynLib(scDD, .registration = TRUE).
 
 .gene_csr <- function(dat, condition, ref, log = TRUE, inclZero = FALSE) {
-  # dat: genes x cells; returns the CSR-over-genes layout of include/scdd_b200.h
-  keep <- if (inclZero) matrix(TRUE, nrow(dat), ncol(dat)) else dat > 0
-  tk <- t(keep)                                   # cell order within each gene
-  vals <- t(dat)[tk]
-  list(vals = if (log) log(vals) else vals,
-       cond01 = as.integer(rep(condition != ref, nrow(dat))[as.vector(tk)]),
-       off = as.double(c(0, cumsum(rowSums(keep)))))
+  # dat: genes x cells; returns the CSR-over-genes layout of include/scdd_b200.h (vals, cond01, off) -- the
+  # library walks R's column-major matrix directly, one threaded pass to count and one to gather
+  storage.mode(dat) <- "double"
+  .Call(C_scdd_gene_csr, dat, nrow(dat), ncol(dat), as.integer(condition != ref), log, inclZero)
 }
+
+# replaces the MAP/MAP1/MAP2 loop of R/scDD.R:528-552; which = -1 (Zhat.combined), 0 (Zhat.c1), 1 (Zhat.c2);
+# labels = unlist of oa$class (combined) or of the c1/c2 classes scattered back to cell order ("class.c")
+zhat_gpu <- function(dat, condition, ref, tofit, off, labels, which = -1L) {
+  storage.mode(dat) <- "double"
+  .Call(C_scdd_zhat, dat, nrow(dat), ncol(dat), as.integer(condition != ref), as.integer(which),
+        as.integer(tofit), off, as.integer(labels))
+}
+
+# replaces  comps.all / comps.c1 / comps.c2 <- luOutlier(...)  of R/scDD.R:335-337 for all genes at once
+luOutlier_gpu <- function(labels, cond01, off, min.size, which = -1L)
+  .Call(C_scdd_cluster_counts, as.integer(labels), as.integer(cond01), off, as.integer(min.size), as.integer(which))
 
 # replaces:  out <- bplapply(1:nrow(...), function(x) genefit(normcounts(SCdat)[tofit[x],]))   R/scDD.R:393
 genefit_gpu <- function(dat, condition, ref, prior, min.size, with.bf = TRUE) {

@@ -102,12 +102,63 @@ SEXP C_scdd_ks(SEXP vals, SEXP off, SEXP cond01) {
     return out;
 }
 
+/* dense matrix -> CSR-over-genes in one threaded pass each (replaces t(dat)[t(dat > 0)] style R code).
+ * dat: numeric genes x cells matrix (column-major, as R stores it); cond01: integer per cell. */
+SEXP C_scdd_gene_csr(SEXP dat, SEXP nrow, SEXP ncol, SEXP cond01, SEXP take_log, SEXP incl_zero) {
+    int ng = asInteger(nrow), nc = asInteger(ncol), iz = asLogical(incl_zero);
+    int32_t *n0 = (int32_t *)R_alloc(ng > 0 ? ng : 1, sizeof(int32_t)), *n1 = (int32_t *)R_alloc(ng > 0 ? ng : 1, sizeof(int32_t));
+    int64_t *o = (int64_t *)R_alloc((size_t)ng + 1, sizeof(int64_t));
+    int rc = scdd_dense_scan(REAL(dat), ng, nc, 1, INTEGER(cond01), n0, n1, NULL, NULL, NULL);
+    if (rc != SCDD_OK) Rf_error("scdd_b200: %s", scdd_last_error());
+    SEXP off = PROTECT(allocVector(REALSXP, (R_xlen_t)ng + 1));
+    o[0] = 0; REAL(off)[0] = 0;
+    for (int g = 0; g < ng; g++) { o[g + 1] = o[g] + (iz ? nc : n0[g] + n1[g]); REAL(off)[g + 1] = (double)o[g + 1]; }
+    SEXP vals = PROTECT(allocVector(REALSXP, (R_xlen_t)o[ng])), c = PROTECT(allocVector(INTSXP, (R_xlen_t)o[ng]));
+    rc = scdd_dense_to_csr(REAL(dat), ng, nc, 1, INTEGER(cond01), NULL, ng, asLogical(take_log), iz, o, REAL(vals), INTEGER(c));
+    if (rc != SCDD_OK) { UNPROTECT(3); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    const char *nm[] = {"vals", "cond01", "off", ""};
+    SEXP out = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(out, 0, vals); SET_VECTOR_ELT(out, 1, c); SET_VECTOR_ELT(out, 2, off);
+    UNPROTECT(4);
+    return out;
+}
+
+/* Zhat matrix of R/scDD.R:528-552 (which = -1 combined, 0 = c1, 1 = c2); tofit: 1-based rows of the fitted genes,
+ * labels: their class labels in CSR order.  Replaces the `for (g in 1:nrow(...))` loop. */
+SEXP C_scdd_zhat(SEXP dat, SEXP nrow, SEXP ncol, SEXP cond01, SEXP which, SEXP tofit, SEXP off, SEXP labels) {
+    int ng = asInteger(nrow), nc = asInteger(ncol), w = asInteger(which), nsel;
+    int64_t *o = offsets(off, &nsel);
+    int32_t *rows = (int32_t *)R_alloc(nsel > 0 ? nsel : 1, sizeof(int32_t));
+    for (int j = 0; j < nsel; j++) rows[j] = INTEGER(tofit)[j] - 1;
+    int cols = 0;
+    for (int c = 0; c < nc; c++) cols += w < 0 || (INTEGER(cond01)[c] != 0) == (w != 0);
+    SEXP Z = PROTECT(allocMatrix(REALSXP, ng, cols));
+    int rc = scdd_labels_to_dense(REAL(dat), ng, nc, 1, INTEGER(cond01), w, rows, nsel, o, INTEGER(labels), REAL(Z));
+    if (rc != SCDD_OK) { UNPROTECT(1); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    UNPROTECT(1);
+    return Z;
+}
+
+/* luOutlier over all genes (R/Cluster_actions.R:25): comps.all (which = -1), comps.c1 (0), comps.c2 (1) */
+SEXP C_scdd_cluster_counts(SEXP labels, SEXP cond01, SEXP off, SEXP min_size, SEXP which) {
+    int ng;
+    int64_t *o = offsets(off, &ng);
+    SEXP out = PROTECT(allocVector(INTSXP, ng));
+    int rc = scdd_cluster_counts(INTEGER(labels), INTEGER(cond01), o, ng, asInteger(min_size), asInteger(which), INTEGER(out));
+    if (rc != SCDD_OK) { UNPROTECT(1); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    UNPROTECT(1);
+    return out;
+}
+
 SEXP C_scdd_device_count(void) { return ScalarInteger(scdd_device_count()); }
 
 static const R_CallMethodDef calls[] = {
     {"C_scdd_fit_observed", (DL_FUNC)&C_scdd_fit_observed, 6},
     {"C_scdd_perm_bf", (DL_FUNC)&C_scdd_perm_bf, 9},
     {"C_scdd_ks", (DL_FUNC)&C_scdd_ks, 3},
+    {"C_scdd_gene_csr", (DL_FUNC)&C_scdd_gene_csr, 6},
+    {"C_scdd_zhat", (DL_FUNC)&C_scdd_zhat, 8},
+    {"C_scdd_cluster_counts", (DL_FUNC)&C_scdd_cluster_counts, 5},
     {"C_scdd_device_count", (DL_FUNC)&C_scdd_device_count, 0},
     {NULL, NULL, 0}};
 

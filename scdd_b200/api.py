@@ -122,26 +122,22 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     if cond is None or len(_unique_in_order(cond)) != 2 or len(cond) != X.shape[1]:
         raise ValueError("Error: Please specify valid condition labels.")
     ref = _unique_in_order(cond)[0]
-    if (X < 0).sum() > 0:
+    # one threaded pass over the matrix: nonzero cells per condition, constant-value flags, negatives
+    nnz0, nnz1, const0, const1, n_negative = hp.dense_scan(X, cond, ref=ref)
+    if n_negative > 0:
         raise ValueError("Error: Negative values for Normalized Expression counts detected. "
                          "Please ensure all counts are non-negative")
     if min_nonzero is None:
         min_nonzero = min_size
     isref = cond == ref
     need = max(min_size, 2, min_nonzero)
-    tofit = np.nonzero(((X[:, isref] > 0).sum(1) >= need) & ((X[:, ~isref] > 0).sum(1) >= need))[0]
+    tofit = np.nonzero((nnz0 >= need) & (nnz1 >= need))[0]
     ngenes = X.shape[0]
     if tofit.size < ngenes:
         msg(f"Notice: {ngenes - tofit.size} genes have less than {min_nonzero} nonzero cells per condition.  "
             f"Skipping these genes.")
-    # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310), vectorised:
-    # length(unique(x[x > 0])) == 1  <=>  min == max over the nonzero entries
-    def _const(rows):
-        nz = rows > 0
-        lo = np.where(nz, rows, np.inf).min(axis=1)
-        hi = np.where(nz, rows, -np.inf).max(axis=1)
-        return nz.any(axis=1) & (lo == hi)
-    skip = _const(X[np.ix_(tofit, np.nonzero(isref)[0])]) | _const(X[np.ix_(tofit, np.nonzero(~isref)[0])])
+    # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310)
+    skip = const0[tofit] | const1[tofit]
     if skip.any():
         msg(f"Notice: {int(skip.sum())} Genes have constant nonzero values.  Skipping these genes.")
         tofit = tofit[~skip]
@@ -151,9 +147,9 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     msg(f"Setting up parallel back-end using {hp.device_count()} GPUs")
     cfg = hp.make_cfg(alpha=prior_param["alpha"], mu0=prior_param["mu0"], s0=prior_param["s0"], a0=prior_param["a0"],
                       b0=prior_param["b0"], min_size=min_size)
-    Xf = X[tofit]
-    logy, c01, off = hp.gene_csr(Xf, cond, ref=ref)
     nf = tofit.size
+    sel = None if nf == ngenes else tofit
+    logy, c01, off = hp.gene_csr(X, cond, ref=ref, genes=sel, nnz=(nnz0 + nnz1)[tofit])
     stats = {}
     if categorize:
         msg("Clustering observed expression data for each gene")
@@ -163,20 +159,14 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     if categorize:
         fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=cfg, with_bf=permutations != 0)
         stats["observed"] = st
-        # luOutlier (R/Cluster_actions.R:25) for every gene at once: label counts per (gene, label)
-        gidx = np.repeat(np.arange(nf), np.diff(off))
-
-        def _lu(labels, mask):
-            cnt = np.bincount(gidx[mask] * 6 + labels[mask], minlength=nf * 6).reshape(nf, 6)
-            return (cnt[:, 1:] >= min_size).sum(axis=1).astype(np.float64)
-        allm = np.ones(gidx.size, dtype=bool)
-        comps_all = _lu(cls_oa, allm)
-        comps_c1 = _lu(cls_c, c01 == 0)
-        comps_c2 = _lu(cls_c, c01 == 1)
+        # luOutlier (R/Cluster_actions.R:25) for every gene at once
+        comps_all = hp.cluster_counts(cls_oa, c01, off, min_size=min_size).astype(np.float64)
+        comps_c1 = hp.cluster_counts(cls_c, c01, off, min_size=min_size, which=0).astype(np.float64)
+        comps_c2 = hp.cluster_counts(cls_c, c01, off, min_size=min_size, which=1).astype(np.float64)
     if permutations == 0:
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")
-        res_ks = testKS(Xf, cond, inclZero=False)
+        res_ks = testKS(X if sel is None else X[tofit], cond, inclZero=False)
         sig = np.nonzero(res_ks["p"] < level)[0]
         pvals = res_ks["p.unadj"]
     else:
@@ -186,6 +176,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         seeds = hp.gene_seeds(seed, nf)
         cdr = None
         if adjust_perms:
+            Xf = X if sel is None else X[tofit]
             C = (Xf > 0).sum(axis=0) / float(nf)                       # R/scDD.R:457
             cdr = np.broadcast_to(C, Xf.shape)[Xf > 0]
         if perm_source == "host":
@@ -208,15 +199,9 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
             cats_all[g] = None if j in sigset else "NS"   # DE/DP/DM/DB/NC labels come from R's classifyDD / feDP
     # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label
     if categorize:
-        MAP = np.ones(X.shape)
-        MAP[X == 0] = 0
-        rows = np.repeat(tofit, np.diff(off))
-        cols = np.nonzero(Xf > 0)[1]
-        MAP[rows, cols] = cls_oa
-        MAPc = np.ones(X.shape)
-        MAPc[X == 0] = 0
-        MAPc[rows, cols] = cls_c
-        MAP1, MAP2 = MAPc[:, isref], MAPc[:, ~isref]
+        MAP = hp.labels_to_dense(X, cond, cls_oa, off, genes=tofit, ref=ref)
+        MAP1 = hp.labels_to_dense(X, cond, cls_c, off, genes=tofit, which=0, ref=ref)
+        MAP2 = hp.labels_to_dense(X, cond, cls_c, off, genes=tofit, which=1, ref=ref)
     else:
         MAP1 = MAP2 = MAP = "Categorize set to FALSE; no clustering provided."
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "dense_host.h"
 
 using namespace scdd;
 
@@ -909,6 +910,54 @@ int32_t scdd_rng_mt_sample_perms(uint32_t seed, int32_t n, int32_t count, int32_
         r_sample_perm(mt, (uint32_t)n, scratch.data(), o);
         for (int i = 0; i < n; i++) o[i] += 1;
     }
+    return SCDD_OK;
+}
+
+// ---------------------------------------------------------------- dense matrix <-> CSR (host marshalling)
+static bool dense_view(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cc, dense::View& v) {
+    if (ngenes < 0 || ncells < 0 || ((!X || !cc) && ngenes * ncells > 0)) return false;
+    v = dense::View{X, ngenes, ncells, col_major != 0};
+    return true;
+}
+
+int32_t scdd_dense_scan(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                        int32_t* nnz0, int32_t* nnz1, uint8_t* const0, uint8_t* const1, int64_t* n_negative) {
+    dense::View v;
+    if (!dense_view(X, ngenes, ncells, col_major, cell_cond01, v)) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    dense::scan(v, cell_cond01, nnz0, nnz1, const0, const1, n_negative);
+    return SCDD_OK;
+}
+
+int32_t scdd_dense_to_csr(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                          const int32_t* genes, int32_t nsel, int32_t take_log, int32_t incl_zero,
+                          const int64_t* gene_off, double* vals, int32_t* cond01) {
+    dense::View v;
+    if (!dense_view(X, ngenes, ncells, col_major, cell_cond01, v) || nsel < 0 || !gene_off ||
+        (gene_off[nsel] > 0 && (!vals || !cond01)))
+        return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    if (!dense::to_csr(v, cell_cond01, genes, nsel, take_log != 0, incl_zero != 0, gene_off, vals, cond01))
+        return fail(SCDD_ERR_BAD_ARG, "gene_off does not match the number of kept cells of the selected genes");
+    return SCDD_OK;
+}
+
+int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
+                             int32_t which, const int32_t* genes, int32_t nsel, const int64_t* gene_off,
+                             const int32_t* labels, double* Z) {
+    dense::View v;
+    if (!dense_view(X, ngenes, ncells, col_major, cell_cond01, v) || nsel < 0 || (ngenes * ncells > 0 && !Z) ||
+        (nsel > 0 && labels && !gene_off))
+        return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    if (!dense::labels_to_dense(v, cell_cond01, which, genes, nsel, gene_off, labels, Z))
+        return fail(SCDD_ERR_BAD_ARG, "gene_off does not match the nonzero cells of the selected genes");
+    return SCDD_OK;
+}
+
+int32_t scdd_cluster_counts(const int32_t* labels, const int32_t* cond01, const int64_t* gene_off, int32_t ngenes,
+                            int32_t min_size, int32_t which, int32_t* counts) {
+    if (ngenes < 0 || (ngenes > 0 && (!gene_off || !counts)) || (ngenes > 0 && gene_off[ngenes] > 0 && !labels) ||
+        (which >= 0 && ngenes > 0 && gene_off[ngenes] > 0 && !cond01))
+        return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    dense::cluster_counts(labels, cond01, gene_off, ngenes, min_size, which, SCDD_GMAX, counts);
     return SCDD_OK;
 }
 

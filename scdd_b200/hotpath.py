@@ -13,26 +13,93 @@ from . import _lib
 from ._lib import FIT_DTYPE, Stats, make_cfg, ScddError  # noqa: F401
 
 
-def gene_csr(normcounts, condition, ref=None, log=True, incl_zero=False):
-    """Dense genes x cells matrix -> the CSR-over-genes layout of the C ABI.
+def _dense(normcounts, condition, ref):
+    """(X, col_major, cell_cond01): the matrix as the C ABI takes it -- C order, or Fortran order (an R matrix) as is."""
+    X = np.asarray(normcounts, dtype=np.float64)
+    if X.ndim != 2:
+        raise ValueError("normcounts must be a genes x cells matrix")
+    col_major = X.flags.f_contiguous and not X.flags.c_contiguous
+    if not col_major:
+        X = np.ascontiguousarray(X)
+    condition = np.asarray(condition)
+    if condition.shape[0] != X.shape[1]:
+        raise ValueError("condition must have one entry per cell")
+    if ref is None:
+        ref = condition[0]
+    return X, int(col_major), np.ascontiguousarray(condition != ref, dtype=np.int32)
+
+
+def dense_scan(normcounts, condition, ref=None):
+    """Per-gene filters of scDD() (R/scDD.R:262, :270-274, :292-298) in one threaded pass over the matrix:
+    returns (nnz0, nnz1, const0, const1, n_negative)."""
+    X, cm, cc = _dense(normcounts, condition, ref)
+    ng, nc = X.shape
+    nnz0, nnz1 = np.zeros(ng, dtype=np.int32), np.zeros(ng, dtype=np.int32)
+    k0, k1 = np.zeros(ng, dtype=np.uint8), np.zeros(ng, dtype=np.uint8)
+    neg = C.c_int64(0)
+    _lib.check(_lib.lib().scdd_dense_scan(X.ctypes.data, ng, nc, cm, cc.ctypes.data, nnz0.ctypes.data, nnz1.ctypes.data,
+                                          k0.ctypes.data, k1.ctypes.data, C.addressof(neg)))
+    return nnz0, nnz1, k0.astype(bool), k1.astype(bool), int(neg.value)
+
+
+def gene_csr(normcounts, condition, ref=None, log=True, incl_zero=False, genes=None, nnz=None):
+    """Dense genes x cells matrix -> the CSR-over-genes layout of the C ABI (scdd_dense_to_csr).
 
     Returns (vals, cond01, gene_off): per gene the (log) nonzero values in cell order
     (`y <- log(y[y>0])`, R/scDD.R:374-375) and 0/1 condition labels (0 = reference = first level,
-    R/scDD.R:258).  incl_zero keeps zeros (testKS(inclZero=TRUE), values not logged)."""
-    X = np.asarray(normcounts, dtype=np.float64)
-    condition = np.asarray(condition)
-    if ref is None:
-        ref = condition[0]
-    c01 = (condition != ref).astype(np.int32)
-    mask = np.ones_like(X, dtype=bool) if incl_zero else (X > 0)
-    counts = mask.sum(axis=1)
-    gene_off = np.zeros(X.shape[0] + 1, dtype=np.int64)
+    R/scDD.R:258).  incl_zero keeps zeros (testKS(inclZero=TRUE), values not logged).
+    genes: optional row subset (0-based); nnz: their nonzero counts if already known from dense_scan."""
+    X, cm, cc = _dense(normcounts, condition, ref)
+    ng, nc = X.shape
+    if genes is not None:
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+    nsel = ng if genes is None else genes.size
+    if incl_zero:
+        counts = np.full(nsel, nc, dtype=np.int64)
+    elif nnz is not None:
+        counts = np.asarray(nnz, dtype=np.int64)
+    else:
+        n0, n1 = dense_scan(X, cc, ref=0)[:2]
+        counts = n0.astype(np.int64) + n1
+        if genes is not None:
+            counts = counts[genes]
+    gene_off = np.zeros(nsel + 1, dtype=np.int64)
     np.cumsum(counts, out=gene_off[1:])
-    vals = X[mask]                      # row-major boolean indexing keeps cell order within each gene
-    if log:
-        vals = np.log(vals)
-    cond01 = np.broadcast_to(c01, X.shape)[mask].astype(np.int32)
-    return np.ascontiguousarray(vals), np.ascontiguousarray(cond01), gene_off
+    vals = np.empty(int(gene_off[-1]), dtype=np.float64)
+    cond01 = np.empty(int(gene_off[-1]), dtype=np.int32)
+    _lib.check(_lib.lib().scdd_dense_to_csr(X.ctypes.data, ng, nc, cm, cc.ctypes.data, _lib.ptr(genes), nsel,
+                                            int(bool(log)), int(bool(incl_zero)), gene_off.ctypes.data,
+                                            vals.ctypes.data, cond01.ctypes.data))
+    return vals, cond01, gene_off
+
+
+def labels_to_dense(normcounts, condition, labels, gene_off, genes=None, which=-1, ref=None):
+    """Zhat matrix (R/scDD.R:528-552): 0 where the count is zero, the class label on the nonzero cells of the fitted
+    genes, 1 elsewhere.  which = 0 / 1 keeps only that condition's columns."""
+    X, cm, cc = _dense(normcounts, condition, ref)
+    ng, nc = X.shape
+    ncols = nc if which < 0 else int((cc != 0).sum() if which else (cc == 0).sum())
+    Z = np.empty((ng, ncols), dtype=np.float64, order="F" if cm else "C")
+    if genes is not None:
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    nsel = gene_off.size - 1
+    assert genes is None or genes.size == nsel
+    _lib.check(_lib.lib().scdd_labels_to_dense(X.ctypes.data, ng, nc, cm, cc.ctypes.data, int(which), _lib.ptr(genes),
+                                               nsel, gene_off.ctypes.data, labels.ctypes.data, Z.ctypes.data))
+    return Z
+
+
+def cluster_counts(labels, cond01, gene_off, min_size=3, which=-1):
+    """luOutlier per gene (R/Cluster_actions.R:25): number of classes with at least min_size members."""
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    cond01 = np.ascontiguousarray(cond01, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    out = np.zeros(gene_off.size - 1, dtype=np.int32)
+    _lib.check(_lib.lib().scdd_cluster_counts(labels.ctypes.data, cond01.ctypes.data, gene_off.ctypes.data,
+                                              gene_off.size - 1, int(min_size), int(which), out.ctypes.data))
+    return out
 
 
 def _prep(vals, cond01, gene_off):

@@ -1,5 +1,6 @@
 """CPU checks of the host-side mirror (no GPU): CSR marshalling, BH adjustment, argument validation,
 workload generator, gene sharding; plus a world_size-2 gloo run of the sharded path against the oracle."""
+import math
 import os
 import subprocess
 import sys
@@ -20,10 +21,77 @@ def test_gene_csr_matches_reference_preprocessing(golden_dir):
     logy, c01, off = hp.gene_csr(X, cond)
     for g in (0, 7, 29):
         y = X[g]
-        assert np.array_equal(logy[off[g]:off[g + 1]], np.log(y[y > 0]))          # R/scDD.R:374-375
+        assert logy[off[g]:off[g + 1]].tolist() == [math.log(v) for v in y[y > 0]]    # R/scDD.R:374-375, libm log
         assert np.array_equal(c01[off[g]:off[g + 1]], (cond[y > 0] != cond[0]).astype(np.int32))
     v, c, o = hp.gene_csr(X, cond, log=False, incl_zero=True)
     assert v.size == X.size and o[-1] == X.size
+
+
+def _zhat_by_loops(X, cond, ref, sel, off, lab, which):
+    """R/scDD.R:528-552 spelled out gene by gene."""
+    M = np.ones(X.shape)
+    M[X == 0] = 0
+    for j, g in enumerate(sel):
+        M[g][X[g] != 0] = lab[off[j]:off[j + 1]]
+    return M if which < 0 else M[:, (cond != ref) == bool(which)]
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_dense_helpers_match_the_reference_loops(order):
+    """scdd_dense_scan / scdd_dense_to_csr / scdd_labels_to_dense / scdd_cluster_counts against the per-gene R
+    expressions they replace (R/scDD.R:262, :270-274, :292-298, :374-375, :528-552, R/Cluster_actions.R:25),
+    for a numpy (row-major) and an R-style (column-major) matrix."""
+    rng = np.random.default_rng(1)
+    X = rng.gamma(2.0, 3.0, (300, 57))
+    X[rng.random(X.shape) < 0.4] = 0
+    X[5, :] = 0                                  # all-zero gene
+    X[7, :] = np.where(X[7] > 0, 3.5, 0)         # constant nonzero values in both conditions
+    cond = np.array(["b", "a"])[rng.integers(0, 2, 57)]
+    ref = cond[0]
+    isref = cond == ref
+    XX = np.asarray(X, order=order)
+    n0, n1, k0, k1, neg = hp.dense_scan(XX, cond, ref=ref)
+    assert neg == 0
+    assert np.array_equal(n0, (X[:, isref] > 0).sum(1)) and np.array_equal(n1, (X[:, ~isref] > 0).sum(1))
+
+    def const(rows):
+        return np.array([len(np.unique(r[r > 0])) == 1 for r in rows])
+    assert np.array_equal(k0, const(X[:, isref])) and np.array_equal(k1, const(X[:, ~isref]))
+    assert k0[7] and k1[7] and not k0[5]
+    Xn = XX.copy(order=order)
+    Xn[3, 4] = -1.0
+    Xn[200, 0] = -2.0
+    assert hp.dense_scan(Xn, cond, ref=ref)[4] == 2
+
+    sel = np.array([1, 2, 3, 10, 200, 299], dtype=np.int32)
+    for genes in (None, sel):
+        rows = np.arange(300) if genes is None else genes
+        v, c, o = hp.gene_csr(XX, cond, ref=ref, genes=genes)
+        assert np.array_equal(np.diff(o), (X[rows] > 0).sum(1))
+        for j, g in enumerate(rows):
+            y = X[g]
+            assert v[o[j]:o[j + 1]].tolist() == [math.log(t) for t in y[y > 0]]
+            assert np.array_equal(c[o[j]:o[j + 1]], (cond[y > 0] != ref).astype(np.int32))
+        vz, cz, oz = hp.gene_csr(XX, cond, ref=ref, genes=genes, log=False, incl_zero=True)
+        assert np.array_equal(vz.reshape(len(rows), 57), X[rows]) and np.array_equal(np.diff(oz), np.full(len(rows), 57))
+        assert np.array_equal(cz.reshape(len(rows), 57), np.broadcast_to((cond != ref).astype(np.int32), (len(rows), 57)))
+        lab = rng.integers(1, 6, v.size).astype(np.int32)
+        for which in (-1, 0, 1):
+            Z = hp.labels_to_dense(XX, cond, lab, o, genes=genes, which=which, ref=ref)
+            assert Z.flags.f_contiguous if order == "F" else Z.flags.c_contiguous
+            assert np.array_equal(Z, _zhat_by_loops(X, cond, ref, rows, o, lab, which))
+            cnt = hp.cluster_counts(lab, c, o, min_size=3, which=which)
+            for j in range(len(rows)):
+                l, cc = lab[o[j]:o[j + 1]], c[o[j]:o[j + 1]]
+                assert cnt[j] == api.luOutlier(l if which < 0 else l[cc == which], 3)
+    with pytest.raises(hp.ScddError, match="gene_off does not match"):
+        hp.gene_csr(XX, cond, ref=ref, nnz=np.full(300, 2))
+    with pytest.raises(hp.ScddError, match="gene_off does not match"):
+        hp.labels_to_dense(XX, cond, np.ones(600, dtype=np.int32), np.arange(0, 602, 2), ref=ref)
+    with pytest.raises(ValueError, match="one entry per cell"):
+        hp.dense_scan(XX, cond[:-1])
+    v, c, o = hp.gene_csr(np.zeros((0, 57)), cond)
+    assert v.size == 0 and o.tolist() == [0]
 
 
 def test_p_adjust_bh():
