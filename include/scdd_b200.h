@@ -115,6 +115,20 @@ int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t*
 int32_t scdd_ks(const double* vals, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
                 int32_t old_pvalue, double* D, double* p, scdd_stats* stats);
 
+/* ---- feDP:  R/classify.dd.R:314-383, the follow-up test of the genes the permutation test did not flag ----
+ * Inputs are the gene block plus the class vectors scdd_fit_observed returned (cls_oa, cls_c).  Per gene:
+ *   p_shift : unadjusted p-value of a mean shift of log-nonzero expression between the conditions --
+ *             t.test(y ~ factor(cond)) (Welch, :353), or with cdr != NULL (adjust.perms) the condition coefficient
+ *             of lm(y ~ cdr0 + factor(cond)) (:351).  NaN where the reference would jitter with runif (:345-347).
+ *   p_fisher: fisher.test(table(oa class, cond)) over the non-outlier clusters (findOutliers, :360-365) when
+ *             luOutlier(c1) == luOutlier(c2) == luOutlier(oa) > 1 (:358), NaN otherwise.  Exact enumeration of
+ *             the r x 2 tables (r <= 5) on the device; stats->failed_sets counts tables too large to enumerate.
+ *   counts3 : (nullable) [3*ngenes] luOutlier of oa, c1, c2 (:327-329).
+ * BH adjustment and the NS / DP / NC labelling (:377-382) are a few vector operations left to the caller. */
+int32_t scdd_fedp(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                  const int32_t* cls_oa, const int32_t* cls_c, const double* cdr, int32_t min_size,
+                  double* p_shift, double* p_fisher, int32_t* counts3, scdd_stats* stats);
+
 /* ---- R's RNG on the host (what the R shim gets for free from R itself) ----
  * scdd_rng_gene_seeds: the L'Ecuyer-CMRG state BiocParallel hands to element i of
  * bplapply(seq_len(ngenes), ..., BPPARAM = param) for RNGseed = seed:
@@ -178,6 +192,8 @@ int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out);
 int32_t scdd_selftest_exp(const double* x, int32_t n, double* out);
 /* softmax of G <= 5 log-terms exactly as the E-step evaluates it; logsumexp may be NULL */
 int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp);
+/* the host-side tail of scdd_fedp: out[i] = 2 * pt(-|t[i]|, df[i]) */
+int32_t scdd_selftest_student_p(const double* t, const double* df, int32_t n, double* out);
 /* measured fp64 FMA throughput of the device (TFLOP/s, DFMA = 2 flop), used as the roofline denominator */
 double scdd_measure_fp64_peak(int32_t device, double* sm_clock_mhz_out);
 

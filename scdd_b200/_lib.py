@@ -57,7 +57,7 @@ EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set
            "scdd_fit_observed", "scdd_perm_bf", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
            "scdd_plan_stats", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax",
-           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts"]
+           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
 
 
 def lib_path():
@@ -103,6 +103,8 @@ def lib():
     L.scdd_dense_to_csr.argtypes = [vp, i64, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
     L.scdd_labels_to_dense.argtypes = [vp, i64, i64, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp, vp]
     L.scdd_cluster_counts.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.scdd_fedp.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(Stats)]
+    L.scdd_selftest_student_p.argtypes = [vp, vp, C.c_int32, vp]
     _LIB = L
     return L
 

@@ -9,11 +9,13 @@ names, argument meaning, error strings and result columns as the R functions it 
     results()   R/helper.R:62-66
 
 All numerical work of the hot path happens in libscdd_b200.so (CUDA); this module contains no fitting code.
+    feDP()      R/classify.dd.R:314-383  (the follow-up test of the non-significant genes)
+
 What stays in R in a real deployment and is therefore NOT reproduced here (out of scope /
-"next"): classifyDD and feDP (DDcategory labels of individual genes; they consume R's RNG via rt/runif) and
-testZeroes (arm::bayesglm).  `DDcategory` is therefore "NS" for non-significant genes and None (NA) for
-significant ones; the R shim in r/ keeps calling the reference's own classifyDD / feDP on the lists this
-path produces.
+"next"): classifyDD (DE/DP/DM/DB labels of individual genes; Monte-Carlo with R's rt) and testZeroes
+(arm::bayesglm).  `DDcategory` is therefore "NS" / "DP" for the genes feDP settles, and None (NA) for the genes
+the reference hands to classifyDD (the significant ones and feDP's "NC" candidates); the R shim in r/ keeps
+calling the reference's own classifyDD on the lists this path produces.
 """
 import numpy as np
 
@@ -90,6 +92,30 @@ def testKS(dat, condition, inclZero=True, numDE=None, DEIndex=None, rownames=Non
     return out
 
 
+def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3):
+    """R/classify.dd.R:314-383 over the CSR gene block (what `pe_mat[tofit, ]`, `condition` and the oa / c1 / c2
+    class vectors are to the R function).  sig_genes: 0-based indices of the significant genes; cdr given means
+    adjust.perms = TRUE.  Returns (ns_genes, pval_ns, cat): the BH-adjusted mean-shift p-values of the
+    non-significant genes and their names "NS" / "DP" / "NC" -- R's `names(pval.ns) <- cat`.
+    R quirk kept: with no significant gene `(1:nrow(pe_mat))[-sig_genes]` is EMPTY, so nothing is tested."""
+    ng = len(gene_off) - 1
+    thresh = 0.025 if testZeroes else 0.05
+    sig = np.zeros(ng, dtype=bool)
+    sig[np.asarray(sig_genes, dtype=np.int64)] = True
+    ns = np.nonzero(~sig)[0] if sig.any() else np.zeros(0, dtype=np.int64)
+    if ns.size == 0:
+        return ns, np.zeros(0), np.zeros(0, dtype=object)
+    p_shift, p_fisher, cnt, _ = hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr, min_size=min_size)
+    pv = p_adjust_BH(p_shift[ns])
+    with np.errstate(invalid="ignore"):
+        cat = np.where(p_fisher[ns] < 0.05, "DP", "NS").astype(object)       # :366-373 (NaN: test not run -> "NS")
+        low = pv < thresh
+    c = cnt[ns]
+    cat[low & (cat != "DP")] = "NC"                                          # :378
+    cat[low & (c[:, 1] == c[:, 2]) & (c[:, 1] == c[:, 0]) & (c[:, 1] > 1)] = "DP"   # :379
+    return ns, pv, cat
+
+
 def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=False, param=None,
          parallelBy=("Genes", "Permutations"), condition="condition", min_size=3, min_nonzero=None, level=0.05,
          categorize=True, perm_source="device", verbose=True):
@@ -163,6 +189,11 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         comps_all = hp.cluster_counts(cls_oa, c01, off, min_size=min_size).astype(np.float64)
         comps_c1 = hp.cluster_counts(cls_c, c01, off, min_size=min_size, which=0).astype(np.float64)
         comps_c2 = hp.cluster_counts(cls_c, c01, off, min_size=min_size, which=1).astype(np.float64)
+    cdr = None
+    if adjust_perms:
+        Xf = X if sel is None else X[tofit]
+        C = (Xf > 0).sum(axis=0) / float(nf)                           # R/scDD.R:457, R/classify.dd.R:331
+        cdr = np.broadcast_to(C, Xf.shape)[Xf > 0]
     if permutations == 0:
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")
@@ -174,11 +205,6 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         msg(f"Parallelizing by {parallelBy}")
         seed = int(param.get("RNGseed", 1))
         seeds = hp.gene_seeds(seed, nf)
-        cdr = None
-        if adjust_perms:
-            Xf = X if sel is None else X[tofit]
-            C = (Xf > 0).sum(axis=0) / float(nf)                       # R/scDD.R:457
-            cdr = np.broadcast_to(C, Xf.shape)[Xf > 0]
         if perm_source == "host":
             perm_idx = np.concatenate([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), permutations)[0].ravel()
                                        for g in range(nf)]) if nf else np.zeros(0, dtype=np.int32)
@@ -194,9 +220,18 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     cats_all = [None] * ngenes
     if categorize:
         msg("Classifying significant genes into patterns")
-        sigset = set(sig.tolist())
+        # R/scDD.R:485-512: significant genes go to classifyDD (R; None here), the others start as "NS" and feDP
+        # promotes some to "DP" or to classifyDD candidates ("NC" with adjusted p > level -> None here)
+        cats = np.full(nf, "NS", dtype=object)
+        cats[sig] = None
+        ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=False, cdr=cdr if adjust_perms else None,
+                             min_size=min_size)
+        cats[ns] = cat_ns
+        with np.errstate(invalid="ignore"):
+            to_classify = (p_adjust_BH(pvals) > level) & (cats == "NC")
+        cats[to_classify] = None
         for j, g in enumerate(tofit):
-            cats_all[g] = None if j in sigset else "NS"   # DE/DP/DM/DB/NC labels come from R's classifyDD / feDP
+            cats_all[g] = cats[j]
     # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label
     if categorize:
         MAP = hp.labels_to_dense(X, cond, cls_oa, off, genes=tofit, ref=ref)

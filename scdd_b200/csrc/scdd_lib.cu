@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fedp.cuh"
 #include "dense_host.h"
 
 using namespace scdd;
@@ -870,6 +871,187 @@ int32_t scdd_ks(const double* vals, const int64_t* gene_off, const int32_t* cond
         }
         return SCDD_OK;
     });
+}
+
+// ---------------------------------------------------------------- feDP (R/classify.dd.R:314-383)
+// two-sided Student p-value 2 * pt(-|t|, df) = I_{df/(df+t^2)}(df/2, 1/2): continued fraction of the regularised
+// incomplete beta function (modified Lentz), with R's normal approximation for df > 4e5 (nmath/pt.c)
+static double beta_cf(double a, double b, double x) {
+    const double tiny = 1e-300, eps = 1e-16;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (std::fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 200000; m++) {
+        double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (std::fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (std::fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (std::fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (std::fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (std::fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+
+static double student_two_sided(double t, double df) {
+    if (std::isnan(t) || std::isnan(df) || !(df > 0)) return NAN;
+    const double t2 = t * t;
+    if (t2 == 0) return 1.0;
+    if (std::isinf(t2)) return 0.0;
+    if (df > 4e5) {
+        double val = 1.0 / (4.0 * df);
+        return std::erfc(std::fabs(t) * (1.0 - val) / std::sqrt(1.0 + t2 * 2.0 * val) / std::sqrt(2.0));
+    }
+    const double a = 0.5 * df, b = 0.5;
+    const double lx = -std::log1p(t2 / df), l1x = std::log(t2 / (df + t2));   // log x, log(1 - x), x = df/(df+t^2)
+    const double x = std::exp(lx), x1 = t2 / (df + t2);
+    // log Beta(a, 1/2) = lgamma(1/2) - [lgamma(a + 1/2) - lgamma(a)]; the bracket by its asymptotic series for large a
+    // (the difference of two lgammas of magnitude a log a loses ~ log10(a log a) digits)
+    double dl;
+    if (a >= 20.0) {
+        const double i1 = 1.0 / a, i2 = i1 * i1;
+        dl = 0.5 * std::log(a) + i1 * (-1.0 / 8 + i2 * (1.0 / 192 + i2 * (-1.0 / 640 + i2 * (17.0 / 14336 - i2 * (31.0 / 18432)))));
+    } else {
+        dl = std::lgamma(a + b) - std::lgamma(a);
+    }
+    const double lbeta = 0.57236494292470008707 - dl;   // lgamma(1/2) = log(sqrt(pi))
+    const double front = std::exp(a * lx + b * l1x - lbeta);
+    if (x < (a + 1.0) / (a + b + 2.0)) return std::min(1.0, front * beta_cf(a, b, x) / a);
+    return std::min(1.0, std::max(0.0, 1.0 - front * beta_cf(b, a, x1) / b));
+}
+
+int32_t scdd_fedp(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                  const int32_t* cls_oa, const int32_t* cls_c, const double* cdr, int32_t min_size,
+                  double* p_shift, double* p_fisher, int32_t* counts3, scdd_stats* stats) {
+    scdd_cfg cfg;
+    scdd_default_cfg(&cfg);
+    int rc = check_common(logy, gene_off, cond01, ngenes, &cfg);
+    if (rc) return rc;
+    if (ngenes > 0 && (!cls_oa || !cls_c || !p_shift || !p_fisher)) return fail(SCDD_ERR_BAD_ARG, "null pointer");
+    if (ngenes == 0) return SCDD_OK;
+    return guarded([&]() -> int {
+        std::vector<int> devs = active_devices();
+        CK(cudaSetDevice(devs[0]));
+        cudaStream_t s;
+        CK(cudaStreamCreate(&s));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+        const int64_t base = gene_off[0];
+        const size_t nnz = (size_t)(gene_off[ngenes] - base);
+        std::vector<int64_t> h_off(gene_off, gene_off + ngenes + 1);
+        int max_n = 0;
+        for (int g = 0; g <= ngenes; g++) h_off[g] -= base;
+        for (int g = 0; g < ngenes; g++) max_n = std::max<int>(max_n, (int)(h_off[g + 1] - h_off[g]));
+        DevBuf<double> d_y, d_cdr, d_lf, d_part;
+        DevBuf<int64_t> d_off;
+        DevBuf<int32_t> d_cond, d_oa, d_c;
+        DevBuf<FedpGene> d_out;
+        DevBuf<FisherJob> d_jobs;
+        d_y.alloc(nnz); d_off.alloc(ngenes + 1); d_cond.alloc(nnz); d_oa.alloc(nnz); d_c.alloc(nnz); d_out.alloc(ngenes);
+        cudaEvent_t t0, t1;
+        CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        CK(cudaEventRecord(t0, s));
+        CK(cudaMemcpyAsync(d_y.p, logy + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_off.p, h_off.data(), (ngenes + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_cond.p, cond01 + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_oa.p, cls_oa + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_c.p, cls_c + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (cdr) {
+            d_cdr.alloc(nnz);
+            CK(cudaMemcpyAsync(d_cdr.p, cdr + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+        }
+        int n_sm = 0;
+        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devs[0]));
+        const int wpb = 8;
+        const int blocks = std::min((ngenes + wpb - 1) / wpb, n_sm * 8);
+        fedp_stats_kernel<<<blocks, wpb * 32, 0, s>>>(d_y.p, d_off.p, d_cond.p, d_oa.p, d_c.p, cdr ? d_cdr.p : nullptr,
+                                                      ngenes, min_size, d_out.p);
+        CK(cudaGetLastError());
+        std::vector<FedpGene> h(ngenes);
+        CK(cudaMemcpyAsync(h.data(), d_out.p, ngenes * sizeof(FedpGene), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        // ---- Fisher jobs: rows sorted ascending so the two largest are the inner / dependent dimensions;
+        // tables whose enumeration is long are split over several CTAs (partials summed here in job order)
+        std::vector<FisherJob> jobs;
+        std::vector<int> job_gene;
+        const long long CHUNK = 1LL << 22, MAX_JOBS = 1LL << 20;
+        double skipped = 0;
+        for (int g = 0; g < ngenes; g++) {
+            p_fisher[g] = NAN;
+            const FedpGene& f = h[g];
+            if (f.r < 2) continue;
+            int ord[SCDD_GMAX];
+            for (int i = 0; i < f.r; i++) ord[i] = i;
+            std::stable_sort(ord, ord + f.r, [&](int x, int y) { return f.row[x] < f.row[y]; });
+            FisherJob jb{};
+            jb.r = f.r; jb.c0 = f.c0;
+            for (int i = 0; i < f.r; i++) { jb.row[i] = f.row[ord[i]]; jb.a[i] = f.a[ord[i]]; }
+            jb.tol = f.r == 2 ? std::log1p(1e-7) : 3.45254e-7;
+            long double items = (jb.row[f.r - 2] + FISHER_SEG) / FISHER_SEG;
+            for (int i = 0; i < f.r - 2; i++) items *= (long double)(jb.row[i] + 1);
+            if (items / CHUNK + jobs.size() >= (long double)MAX_JOBS) { skipped++; continue; }
+            const long long it = (long long)items;
+            for (long long b0 = 0; b0 < it; b0 += CHUNK) {
+                jb.slot = (int32_t)jobs.size();
+                jb.item_begin = b0; jb.item_end = std::min(it, b0 + CHUNK);
+                jobs.push_back(jb);
+                job_gene.push_back(g);
+            }
+        }
+        if (!jobs.empty()) {
+            std::vector<double> lf(max_n + 1);
+            for (int i = 0; i <= max_n; i++) lf[i] = std::lgamma((double)i + 1.0);
+            d_lf.alloc(lf.size()); d_jobs.alloc(jobs.size()); d_part.alloc(jobs.size());
+            CK(cudaMemcpyAsync(d_lf.p, lf.data(), lf.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(FisherJob), cudaMemcpyHostToDevice, s));
+            const int grid = (int)std::min<size_t>(jobs.size(), (size_t)n_sm * 8);
+            fisher_kernel<<<grid, FISHER_THREADS, 0, s>>>(d_jobs.p, (int)jobs.size(), d_lf.p, d_part.p);
+            CK(cudaGetLastError());
+            std::vector<double> part(jobs.size());
+            CK(cudaMemcpyAsync(part.data(), d_part.p, jobs.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(t1, s));
+            CK(cudaStreamSynchronize(s));
+            for (size_t j = 0; j < jobs.size(); j++) {
+                double& p = p_fisher[job_gene[j]];
+                p = std::isnan(p) ? part[j] : p + part[j];
+            }
+        } else {
+            CK(cudaEventRecord(t1, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        double undefined = 0;
+        for (int g = 0; g < ngenes; g++) {
+            p_shift[g] = student_two_sided(h[g].tstat, h[g].df);
+            if (h[g].flag & 1) { p_shift[g] = NAN; undefined++; }   // the reference would jitter with runif here
+            if (counts3) { counts3[3 * g] = h[g].c_oa; counts3[3 * g + 1] = h[g].c_c1; counts3[3 * g + 2] = h[g].c_c2; }
+        }
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, t0, t1));
+            stats->total_ms = ms;
+            stats->fit_sets = (double)jobs.size();
+            stats->const_sets = undefined;
+            stats->failed_sets = skipped;
+            stats->h2d_bytes = (double)nnz * (20 + (cdr ? 8 : 0)) + (ngenes + 1) * 8.0;
+            stats->d2h_bytes = (double)ngenes * sizeof(FedpGene);
+        }
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+        return SCDD_OK;
+    });
+}
+
+int32_t scdd_selftest_student_p(const double* t, const double* df, int32_t n, double* out) {
+    if (n < 0 || (n > 0 && (!t || !df || !out))) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    for (int i = 0; i < n; i++) out[i] = student_two_sided(t[i], df[i]);
+    return SCDD_OK;
 }
 
 // ---------------------------------------------------------------- host RNG helpers

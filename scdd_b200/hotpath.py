@@ -176,6 +176,26 @@ def ks(vals, cond01, gene_off, old_pvalue=False):
     return D, p
 
 
+def fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=None, min_size=3):
+    """Per-gene pieces of feDP (R/classify.dd.R:337-374) for every gene of the block: returns
+    (p_shift, p_fisher, counts[ngenes, 3] = luOutlier of oa / c1 / c2, stats)."""
+    logy, cond01, gene_off = _prep(logy, cond01, gene_off)
+    cls_oa = np.ascontiguousarray(cls_oa, dtype=np.int32)
+    cls_c = np.ascontiguousarray(cls_c, dtype=np.int32)
+    assert cls_oa.size == logy.size and cls_c.size == logy.size
+    if cdr is not None:
+        cdr = np.ascontiguousarray(cdr, dtype=np.float64)
+        assert cdr.size == logy.size
+    ng = gene_off.size - 1
+    p_shift, p_fisher = np.zeros(ng), np.zeros(ng)
+    counts = np.zeros((ng, 3), dtype=np.int32)
+    st = Stats()
+    _lib.check(_lib.lib().scdd_fedp(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, cls_oa.ctypes.data,
+                                    cls_c.ctypes.data, _lib.ptr(cdr), int(min_size), p_shift.ctypes.data,
+                                    p_fisher.ctypes.data, counts.ctypes.data, C.byref(st)))
+    return p_shift, p_fisher, counts, st.as_dict()
+
+
 def gene_seeds(seed, ngenes):
     """L'Ecuyer-CMRG state of every bplapply element for RNGseed = seed (see scdd_rng_gene_seeds)."""
     out = np.zeros((ngenes, 6), dtype=np.uint32)
