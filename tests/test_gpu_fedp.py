@@ -85,17 +85,17 @@ def test_fedp_rx2_tables_and_empty_sig():
 
 
 def test_fedp_larger_tables_are_split_and_deterministic():
-    """2 000-cell genes: 2 x 2 tables are a single job, a 4-cluster table is enumerated by several CTAs; results are
+    """2 400-cell genes: 2 x 2 tables are a single job, a 4-cluster table is enumerated by several CTAs; results are
     bitwise reproducible and match the restatement"""
     rng = np.random.default_rng(10)
-    nc = 2000
+    nc = 2400
     cond = np.repeat([0, 1], nc // 2)
     X = np.exp(rng.normal(2.0, 0.7, (3, nc)))
     logy, c01, off = hp.gene_csr(X, cond)
     cls = np.zeros(logy.size, dtype=np.int32)
     cls[off[0]:off[1]] = 1 + (rng.random(nc) < 0.4 + 0.05 * cond)
     cls[off[1]:off[2]] = rng.integers(1, 4, nc)
-    cls[off[2]:off[3]] = rng.integers(1, 5, nc)          # 4 clusters of ~500: ~4.3e6 work items, more than one job
+    cls[off[2]:off[3]] = rng.integers(1, 5, nc)          # 4 clusters of ~600: ~6.9e6 work items, more than one job
     a = hp.fedp(logy, c01, off, cls, cls)
     b = hp.fedp(logy, c01, off, cls, cls)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
