@@ -74,3 +74,21 @@ testKS_gpu <- function(dat, condition, inclZero = TRUE) {
   g <- .gene_csr(dat[, keep, drop = FALSE], condition[keep], lev[1], log = FALSE, inclZero = inclZero)
   .Call(C_scdd_ks, g$vals, g$off, g$cond01)$p
 }
+
+# replaces feDP(), R/classify.dd.R:314-383: the per-gene loop runs on the device, the labelling (:377-382) stays R.
+# g: the .gene_csr() list of pe_mat; fit: the list C_scdd_fit_observed returned (class.oa, class.c); C: the cellular
+# detection rate per cell when adjust.perms (else NULL).  NaN p.shift marks genes where the reference would jitter
+# with runif(): those few are recomputed by the reference's own loop body.
+feDP_gpu <- function(g, fit, sig_genes, nrow_pe, C = NULL, testZeroes = FALSE, min.size = 3, keep = NULL) {
+  pval.thresh <- if (testZeroes) 0.025 else 0.05
+  cdr <- if (is.null(C)) NULL else as.double(rep(C, nrow_pe)[keep])   # keep = as.vector(t(pe_mat > 0))
+  r <- .Call(C_scdd_fedp, g$vals, g$off, g$cond01, fit$class.oa, fit$class.c, cdr, as.integer(min.size))
+  ns_genes <- (1:nrow_pe)[-sig_genes]
+  cnt <- r$counts[, ns_genes, drop = FALSE]
+  cat <- ifelse(!is.na(r$p.fisher[ns_genes]) & r$p.fisher[ns_genes] < 0.05, "DP", "NS")
+  pval.ns <- p.adjust(r$p.shift[ns_genes], method = "BH")
+  cat[pval.ns < pval.thresh & cat != "DP"] <- "NC"
+  cat[pval.ns < pval.thresh & cnt[2, ] == cnt[3, ] & cnt[2, ] == cnt[1, ] & cnt[2, ] > 1] <- "DP"
+  names(pval.ns) <- cat
+  pval.ns
+}

@@ -150,6 +150,24 @@ SEXP C_scdd_cluster_counts(SEXP labels, SEXP cond01, SEXP off, SEXP min_size, SE
     return out;
 }
 
+/* feDP's per-gene loop (R/classify.dd.R:337-374) for all genes of the block: mean-shift p-value (Welch, or the
+ * lm condition coefficient when cdr is not NULL), Fisher p-value where the clusterings agree (NA otherwise) and the
+ * three luOutlier counts.  labels as returned by C_scdd_fit_observed ("class.oa", "class.c"). */
+SEXP C_scdd_fedp(SEXP logy, SEXP off, SEXP cond01, SEXP cls_oa, SEXP cls_c, SEXP cdr, SEXP min_size) {
+    int ng;
+    int64_t *o = offsets(off, &ng);
+    SEXP ps = PROTECT(allocVector(REALSXP, ng)), pf = PROTECT(allocVector(REALSXP, ng));
+    SEXP cnt = PROTECT(allocMatrix(INTSXP, 3, ng));
+    int rc = scdd_fedp(REAL(logy), o, INTEGER(cond01), ng, INTEGER(cls_oa), INTEGER(cls_c),
+                       isNull(cdr) ? NULL : REAL(cdr), asInteger(min_size), REAL(ps), REAL(pf), INTEGER(cnt), NULL);
+    if (rc != SCDD_OK) { UNPROTECT(3); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    const char *nm[] = {"p.shift", "p.fisher", "counts", ""};
+    SEXP out = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(out, 0, ps); SET_VECTOR_ELT(out, 1, pf); SET_VECTOR_ELT(out, 2, cnt);
+    UNPROTECT(4);
+    return out;
+}
+
 SEXP C_scdd_device_count(void) { return ScalarInteger(scdd_device_count()); }
 
 static const R_CallMethodDef calls[] = {
@@ -159,6 +177,7 @@ static const R_CallMethodDef calls[] = {
     {"C_scdd_gene_csr", (DL_FUNC)&C_scdd_gene_csr, 6},
     {"C_scdd_zhat", (DL_FUNC)&C_scdd_zhat, 8},
     {"C_scdd_cluster_counts", (DL_FUNC)&C_scdd_cluster_counts, 5},
+    {"C_scdd_fedp", (DL_FUNC)&C_scdd_fedp, 7},
     {"C_scdd_device_count", (DL_FUNC)&C_scdd_device_count, 0},
     {NULL, NULL, 0}};
 

@@ -92,7 +92,7 @@ def testKS(dat, condition, inclZero=True, numDE=None, DEIndex=None, rownames=Non
     return out
 
 
-def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3):
+def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3, stats_out=None):
     """R/classify.dd.R:314-383 over the CSR gene block (what `pe_mat[tofit, ]`, `condition` and the oa / c1 / c2
     class vectors are to the R function).  sig_genes: 0-based indices of the significant genes; cdr given means
     adjust.perms = TRUE.  Returns (ns_genes, pval_ns, cat): the BH-adjusted mean-shift p-values of the
@@ -105,7 +105,9 @@ def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr
     ns = np.nonzero(~sig)[0] if sig.any() else np.zeros(0, dtype=np.int64)
     if ns.size == 0:
         return ns, np.zeros(0), np.zeros(0, dtype=object)
-    p_shift, p_fisher, cnt, _ = hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr, min_size=min_size)
+    p_shift, p_fisher, cnt, st = hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr, min_size=min_size)
+    if stats_out is not None:
+        stats_out.update(st)
     pv = p_adjust_BH(p_shift[ns])
     with np.errstate(invalid="ignore"):
         cat = np.where(p_fisher[ns] < 0.05, "DP", "NS").astype(object)       # :366-373 (NaN: test not run -> "NS")
@@ -225,7 +227,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         cats = np.full(nf, "NS", dtype=object)
         cats[sig] = None
         ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=False, cdr=cdr if adjust_perms else None,
-                             min_size=min_size)
+                             min_size=min_size, stats_out=stats.setdefault("feDP", {}))
         cats[ns] = cat_ns
         with np.errstate(invalid="ignore"):
             to_classify = (p_adjust_BH(pvals) > level) & (cats == "NC")

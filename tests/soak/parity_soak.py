@@ -3,7 +3,7 @@
 Reports how many fit-sets / Bayes factors differ beyond the tolerances of BASELINE.json and the near-tie counters.
 usage: parity_soak.py [genes] [perms]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import pyoracle as po
 from scdd_b200 import hotpath as hp

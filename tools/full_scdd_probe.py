@@ -18,3 +18,9 @@ st = out.metadata["_scdd_b200"]["stats"]
 print(f"scDD({ng} genes x 2000 cells, permutations={B}): {dt:.2f} s wall; observed fit kernel {st['observed']['fit_kernel_ms']:.0f} ms; "
       f"permutation fit kernel {st['permutations']['fit_kernel_ms']:.0f} ms, call total {st['permutations']['total_ms']:.0f} ms")
 print("host-side share:", 1 - (st['observed']['fit_kernel_ms'] + st['permutations']['fit_kernel_ms']) / (dt * 1e3))
+fd = st.get("feDP", {})
+if fd:
+    cats = out.metadata["Genes"]["DDcategory"]
+    import collections
+    print(f"feDP on the device: {fd['total_ms']:.1f} ms (H2D + statistics + {fd['fit_sets']:.0f} Fisher jobs + D2H), "
+          f"tables too large: {fd['failed_sets']:.0f}; categories: {dict(collections.Counter(str(c) for c in cats))}")
