@@ -566,6 +566,18 @@ static void fit_observed_one(int dev, const double* logy, const int64_t* off, co
         DevBuf<int32_t> d_oa, d_c;
         d_fits.alloc(3 * (size_t)ng); d_oa.alloc(P.nnz); d_c.alloc(P.nnz);
         P.d_jp.alloc(3 * (size_t)ng);
+        // no measured costs exist for a first look at the data: start the genes with the most cells first, so the
+        // persistent kernel's tail is made of small fit-sets
+        if (ng >= 2 * P.n_sm) {
+            std::vector<int32_t> order(ng);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(),
+                             [&](int32_t x, int32_t y) { return P.h_off[x + 1] - P.h_off[x] > P.h_off[y + 1] - P.h_off[y]; });
+            P.d_gene_order.alloc(ng);
+            CK(cudaMemcpyAsync(P.d_gene_order.p, order.data(), (size_t)ng * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            P.have_order = true;
+        }
         FitArgs a = P.base_args();
         a.nb = 1; a.sets = 3; a.jp = P.d_jp.p;
         a.fits = d_fits.p; a.cls_oa = d_oa.p; a.cls_c = d_c.p;
@@ -955,8 +967,12 @@ int32_t scdd_fedp(const double* logy, const int64_t* gene_off, const int32_t* co
         DevBuf<FedpGene> d_out;
         DevBuf<FisherJob> d_jobs;
         d_y.alloc(nnz); d_off.alloc(ngenes + 1); d_cond.alloc(nnz); d_oa.alloc(nnz); d_c.alloc(nnz); d_out.alloc(ngenes);
-        cudaEvent_t t0, t1;
-        CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        struct Events {
+            cudaEvent_t a = nullptr, b = nullptr;
+            ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+        } ev;
+        CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+        cudaEvent_t t0 = ev.a, t1 = ev.b;
         CK(cudaEventRecord(t0, s));
         CK(cudaMemcpyAsync(d_y.p, logy + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d_off.p, h_off.data(), (ngenes + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
@@ -1043,7 +1059,6 @@ int32_t scdd_fedp(const double* logy, const int64_t* gene_off, const int32_t* co
             stats->h2d_bytes = (double)nnz * (20 + (cdr ? 8 : 0)) + (ngenes + 1) * 8.0;
             stats->d2h_bytes = (double)ngenes * sizeof(FedpGene);
         }
-        cudaEventDestroy(t0); cudaEventDestroy(t1);
         return SCDD_OK;
     });
 }

@@ -17,6 +17,9 @@ dt = time.time() - t0
 st = out.metadata["_scdd_b200"]["stats"]
 print(f"scDD({ng} genes x 2000 cells, permutations={B}): {dt:.2f} s wall; observed fit kernel {st['observed']['fit_kernel_ms']:.0f} ms; "
       f"permutation fit kernel {st['permutations']['fit_kernel_ms']:.0f} ms, call total {st['permutations']['total_ms']:.0f} ms")
+for k in ("observed", "permutations"):
+    print(f"  {k}: {st[k]['fit_sets']:.0f} fit-sets, {st[k]['triples']:.3e} triples, "
+          f"{st[k]['triples'] / (st[k]['fit_kernel_ms'] * 1e-3):.3e} triples/s, em_iters {st[k]['em_iters']:.0f}")
 print("host-side share:", 1 - (st['observed']['fit_kernel_ms'] + st['permutations']['fit_kernel_ms']) / (dt * 1e3))
 fd = st.get("feDP", {})
 if fd:
