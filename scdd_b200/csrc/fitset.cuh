@@ -134,6 +134,9 @@ __device__ __noinline__ int qclass_breaks(const double* xs, int n, int k, double
 }
 
 __device__ double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE];   // source of the per-CTA shared copy, filled by init_exp_table()
+// The CTA's copy: a statically allocated shared array, so that every function (including the non-inlined E-step
+// dispatchers) addresses it as [index * 8 + link-time constant] with no base register and no address arithmetic.
+__shared__ double EXP_TABLE_SH[SCDD_EXP_TABLE_SIZE];
 // constant-bank copies of device_math.cuh's expc:: constants (fetched with LDCU, no per-iteration immediates)
 __constant__ double EXP_TAB_CONST[3] = {2954.639443740597, -0.00033845077175778578, 1.0 / 6.0};
 
@@ -172,14 +175,28 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // ParamsReg keeps them in registers (3G doubles per lane); ParamsSmem re-reads them from the warp's
 // shared-memory block for every point (broadcast loads on the LSU pipe), which frees 6G registers; used for
 // G = 5, where the register file is the scarcer resource (load_params).
-template <int G>
+// 2^((D mod 2048)/2048) from the CTA's table: mask, then one multiply-add forms the shared address
+// (the compiler's own sequence for tab[D & 2047] is shift, and, add).
+__device__ __forceinline__ double exp_table_sh(int D) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(EXP_TABLE_SH);
+    unsigned addr;
+    double T;
+    asm("{ .reg .b32 j; and.b32 j, %1, %2; mad.lo.u32 %0, j, 8, %3; }" : "=r"(addr) : "r"(D), "n"(expc::TMASK), "r"(base));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
+    return T;
+}
+
+template <int G, bool GTAB = false>
 struct ParamsReg {
-    const double* tab;   // 2^(j/2048) table
     double mu[G], nh[G], lc[G];
+    double c0, c1, c2;   // exp constants held in registers for the whole pass (load_consts)
+    // 2^(j/2048): the CTA's shared copy, or (GTAB, label_of outside the fit loop) the global source
+    __device__ __forceinline__ static double lookup(int D) { return GTAB ? EXP_TABLE_GLOBAL[D & expc::TMASK] : exp_table_sh(D); }
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
-    const double* tab;   // 2^(j/2048) table (shared memory)
+    double c0, c1, c2;
+    __device__ __forceinline__ static double lookup(int D) { return exp_table_sh(D); }
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
@@ -235,7 +252,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);                 // term_t
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], prm.c0, MAGIC);                 // term_t
 #pragma unroll
     for (int i = 0; i < N; i++) n[i] = SAT ? term_n(a[i], t[i]) : __double2loint(t[i]);
 #pragma unroll
@@ -243,9 +260,9 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], prm.c1, a[i]);
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], 0.5);                   // term_s
+    for (int i = 0; i < N; i++) p[i] = fma(prm.c2, r[i], 0.5);                   // term_s
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
@@ -256,7 +273,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int k = 0; k < G; k++) {                                                      // term_e
             const int i = u * G + k;
             const int D = max(n[i] - M[u], DMIN);
-            const double T = prm.tab[D & TMASK];
+            const double T = P::lookup(D);
             const double v = fma(T, p[i], T);
             int hi;   // hi(v) + ((D >> TB) << 20) as shift + multiply-add (two integer instructions, not three)
             asm("{ .reg .s32 k; shr.s32 k, %1, %2; mad.lo.s32 %0, k, 1048576, %3; }" : "=r"(hi) : "r"(D), "n"(TB), "r"(__double2hiint(v)));
@@ -342,12 +359,11 @@ struct Team {
 //   mu = mu_old + S(z d)/S(z),  sigsq = S(z q)/S(z) - (S(z d)/S(z))^2
 // which equals mclust's two-pass update in exact arithmetic and needs no stored z matrix.
 // ---------------------------------------------------------------------------------------------
-template <int G, int U, bool SAT, class P>
-__device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
-                                                  double (&C)[G], double& pl, long long& hs) {
-    double e[U * G], d[U * G], q[U * G], S[U];
-    int M[U];
-    estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M);
+// back half of a point: normalise the softmax terms and add the point to the M-step sums
+template <int G, int U>
+__device__ __forceinline__ void accumulate_back(const double (&e)[U * G], const double (&d)[U * G], const double (&q)[U * G],
+                                                const double (&S)[U], const int (&M)[U], double (&A)[G], double (&B)[G],
+                                                double (&C)[G], double& pl, long long& hs) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
         double rs = rcp_sum(S[u]);
@@ -363,42 +379,75 @@ __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P&
     }
 }
 
+template <int G, int U, bool SAT, class P>
+__device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
+                                                  double (&C)[G], double& pl, long long& hs) {
+    double e[U * G], d[U * G], q[U * G], S[U];
+    int M[U];
+    estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M);
+    accumulate_back<G, U>(e, d, q, S, M, A, B, C, pl, hs);
+}
+
 #ifndef SCDD_PARAMS_SMEM
 #define SCDD_PARAMS_SMEM 1
 #endif
 
 #ifndef SCDD_PARAMS_REG_MAXG
-#define SCDD_PARAMS_REG_MAXG 4      // G <= 4: 6G registers are affordable and save 2 shared loads per term (measured +2 %)
+#define SCDD_PARAMS_REG_MAXG 5      // all G: 6G registers save 2 shared loads per term (A/B at 8192 genes: G <= 4 only is 2.3 % slower)
 #endif
+// Loads the three exp constants once and hides their origin from the compiler, which otherwise re-loads them from
+// the constant bank inside every loop iteration (three extra issue slots per point).
+// The three exp constants.  Read from the constant bank the compiler re-loads them inside every loop iteration (three
+// issue slots per point); read from the pad slots of the team's shared parameter block (store_consts, once per
+// kernel) they cannot be re-materialised and stay in registers for the whole pass.
+#ifndef SCDD_PIN_CONSTS
+#define SCDD_PIN_CONSTS 0   // measured 1.9 % slower at 128 registers (the six extra registers cost more than three LDCs)
+#endif
+__device__ __forceinline__ void store_consts(double* pm) {
+    pm[3] = EXP_TAB_CONST[0]; pm[7] = EXP_TAB_CONST[1]; pm[11] = EXP_TAB_CONST[2];
+}
+template <class P>
+__device__ __forceinline__ void load_consts(P& p, const double* pm) {
+#if SCDD_PIN_CONSTS
+    p.c0 = pm[3]; p.c1 = pm[7]; p.c2 = pm[11];
+#else
+    p.c0 = EXP_TAB_CONST[0]; p.c1 = EXP_TAB_CONST[1]; p.c2 = EXP_TAB_CONST[2];
+#endif
+}
+
 template <int G>
-__device__ __forceinline__ auto load_params(const double* pm, const double* tab) {
+__device__ __forceinline__ auto load_params(const double* pm) {
 #if SCDD_PARAMS_SMEM
     if constexpr (G > SCDD_PARAMS_REG_MAXG) {
         ParamsSmem p;
-        p.tab = tab;
         p.addr = (unsigned)__cvta_generic_to_shared(pm);
+        load_consts(p, pm);
         return p;
     } else {
         ParamsReg<G> p;
-        p.tab = tab;
 #pragma unroll
         for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
+        load_consts(p, pm);
         return p;
     }
 #else
     ParamsReg<G> p;
-    p.tab = tab;
 #pragma unroll
     for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
+    load_consts(p, pm);
     return p;
 #endif
 }
 
+#ifndef SCDD_SKEW
+#define SCDD_SKEW 0
+#endif
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
-                                           const double* tab, double (&v)[16]) {
+                                           double (&v)[16]) {
     constexpr int NT = Team<TW>::NT;
-    const auto prm = load_params<G>(pm, tab);
+    const auto prm = load_params<G>(pm);
+    typedef decltype(load_params<G>(pm)) P;
     double A[G], B[G], C[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
@@ -409,18 +458,41 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
     for (int base = 0; base < n; base += CHUNK) {
         const int stop = (n - base < CHUNK) ? n : base + CHUNK;
         double pl = 1.0;
-        int i = base + Team<TW>::tid(lane);
+        // pointer-bumped loops: the load is [register + immediate] and the bound test compares addresses
+        const double* px = xs + base + Team<TW>::tid(lane);
+        const double* const pend = xs + stop;
+#if SCDD_SKEW
+        if (U == 1) {
+            // Software pipeline, two points in flight per thread: the front half of point i+1 (exp terms) is issued
+            // together with the back half of point i (reciprocal, normalisation, sums).  Ping-pong over two register
+            // sets to avoid moves.  Measured slower than the plain loop ("What did not help"): off by default.
+            if (px < pend) {
+                double e0[G], d0[G], q0[G], S0[1], e1[G], d1[G], q1[G], S1[1];
+                int M0[1], M1[1];
+                { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e0, d0, q0, S0, M0); }
 #pragma unroll 1
-        for (; i + NT * (U - 1) < stop; i += NT * U) {
+                for (;;) {
+                    if (!(px < pend)) { accumulate_back<G, 1>(e0, d0, q0, S0, M0, A, B, C, pl, hs); break; }
+                    { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e1, d1, q1, S1, M1); }
+                    accumulate_back<G, 1>(e0, d0, q0, S0, M0, A, B, C, pl, hs);
+                    if (!(px < pend)) { accumulate_back<G, 1>(e1, d1, q1, S1, M1, A, B, C, pl, hs); break; }
+                    { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e0, d0, q0, S0, M0); }
+                    accumulate_back<G, 1>(e1, d1, q1, S1, M1, A, B, C, pl, hs);
+                }
+            }
+        } else
+#endif
+#pragma unroll 1
+        for (; px + NT * (U - 1) < pend; px += NT * U) {
             double x[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) x[u] = xs[i + NT * u];
+            for (int u = 0; u < U; u++) x[u] = px[NT * u];
             accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hs);
         }
         if (U > 1) {
 #pragma unroll 1
-            for (; i < stop; i += NT) {
-                double x[1] = {xs[i]};
+            for (; px < pend; px += NT) {
+                double x[1] = {*px};
                 accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hs);
             }
         }
@@ -437,8 +509,8 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
 // MAP labels of the final z and their statistics: v[0,G) count, [G,2G) sum y, [2G,3G) sum y^2
 template <int G, int TW>
 __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
-                                           const double* tab, double (&v)[16]) {
-    const auto prm = load_params<G>(pm, tab);
+                                           double (&v)[16]) {
+    const auto prm = load_params<G>(pm);
     double cnt[G], sy[G], syy[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { cnt[k] = 0.0; sy[k] = 0.0; syy[k] = 0.0; }
@@ -459,20 +531,20 @@ __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n,
 
 // unroll factor of the point loop: small G has little instruction-level parallelism per point
 #ifndef SCDD_UNROLL_MAXG
-#define SCDD_UNROLL_MAXG 2
+#define SCDD_UNROLL_MAXG 1          // two points per thread per step pay for their registers at no G (A/B: G <= 2 is 0.2 % slower)
 #endif
 template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_MAXG) ? 2 : 1; };
 
 // returns the team total of slot (lane >> 1): the 16 partial sums never leave registers
 template <int TW>
 __device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
-                                              const double* tab, double* red) {
+                                              double* red) {
     double v[16];
     switch (G) {
-        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, tab, v); break;
-        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, tab, v); break;
-        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, tab, v); break;
-        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, tab, v); break;
+        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, v); break;
+        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, v); break;
+        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, v); break;
+        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, v); break;
     }
     return Team<TW>::reduce(v, lane, red);
 }
@@ -480,26 +552,26 @@ __device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, in
 // same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code
 template <int TW>
 __device__ __noinline__ double estep_dispatch_sat(int G, const double* xs, int n, int lane, const double* pm,
-                                                  const double* tab, double* red) {
+                                                  double* red) {
     double v[16];
     switch (G) {
-        case 2: estep_pass<2, 1, TW, true>(xs, n, lane, pm, tab, v); break;
-        case 3: estep_pass<3, 1, TW, true>(xs, n, lane, pm, tab, v); break;
-        case 4: estep_pass<4, 1, TW, true>(xs, n, lane, pm, tab, v); break;
-        default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, tab, v); break;
+        case 2: estep_pass<2, 1, TW, true>(xs, n, lane, pm, v); break;
+        case 3: estep_pass<3, 1, TW, true>(xs, n, lane, pm, v); break;
+        case 4: estep_pass<4, 1, TW, true>(xs, n, lane, pm, v); break;
+        default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, v); break;
     }
     return Team<TW>::reduce(v, lane, red);
 }
 
 template <int TW>
 __device__ __noinline__ double label_dispatch(int G, const double* xs, int n, int lane, const double* pm,
-                                              const double* tab, double* red) {
+                                              double* red) {
     double v[16];
     switch (G) {
-        case 2: label_pass<2, TW>(xs, n, lane, pm, tab, v); break;
-        case 3: label_pass<3, TW>(xs, n, lane, pm, tab, v); break;
-        case 4: label_pass<4, TW>(xs, n, lane, pm, tab, v); break;
-        default: label_pass<5, TW>(xs, n, lane, pm, tab, v); break;
+        case 2: label_pass<2, TW>(xs, n, lane, pm, v); break;
+        case 3: label_pass<3, TW>(xs, n, lane, pm, v); break;
+        case 4: label_pass<4, TW>(xs, n, lane, pm, v); break;
+        default: label_pass<5, TW>(xs, n, lane, pm, v); break;
     }
     return Team<TW>::reduce(v, lane, red);
 }
@@ -512,7 +584,7 @@ __device__ __noinline__ double label_dispatch(int G, const double* xs, int n, in
 // ---------------------------------------------------------------------------------------------
 template <int TW>
 __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
-                                     double* pm, const double* tab, double* red, int extra_mstep) {
+                                     double* pm, double* red, int extra_mstep) {
     typedef Team<TW> T;
     const double eps = DBL_EPSILON, rteps = 1.4901161193847656e-08, tol = 1e-5;
     const double dn = (double)n;
@@ -586,8 +658,8 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         // |t_k| <= |lc_k| + range^2 / (2 sigsq_k) with |lc_k| < 100: below 2^19 for every point iff the smallest
         // variance exceeds range^2 / 2^20; then the integer extraction needs no saturation test (fast pass)
         const bool wide = !__any_sync(FULLMASK, owner && !(sig_own * 1.0e6 > range2));
-        const double t = wide ? estep_dispatch<TW>(G, xs, n, lane, pm, tab, red)
-                              : estep_dispatch_sat<TW>(G, xs, n, lane, pm, tab, red);
+        const double t = wide ? estep_dispatch<TW>(G, xs, n, lane, pm, red)
+                              : estep_dispatch_sat<TW>(G, xs, n, lane, pm, red);
         A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
         hood = slot(t, 3 * G);
         // stop when |hold - hood| / (1 + |hood|) <= tol  (tested in product form: no division on the critical path)
@@ -633,7 +705,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         }
     }
     // MAP labels from the final z (same parameters as the last E-step) and their statistics
-    const double t = label_dispatch<TW>(G, xs, n, lane, pm, tab, red);   // pm still holds the last E-step's parameters
+    const double t = label_dispatch<TW>(G, xs, n, lane, pm, red);   // pm still holds the last E-step's parameters
     double cnt = slot(t, kown), sy = slot(t, G + kown), syy = slot(t, 2 * G + kown);
     if (owner && T::lead()) {
         row->mean[lane] = mean_out;
@@ -909,10 +981,10 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
 // ---------------------------------------------------------------------------------------------
 template <int TW>
 __device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* rows, const DevCfg& cfg, WarpStats* st,
-                                       double* pm, const double* tab, double* red) {
+                                       double* pm, double* red) {
     typedef Team<TW> T;
     fit_row1<TW>(xs, n, lane, &rows[0], red);
-    for (int G = 2; G <= GMAX; G++) fit_row<TW>(G, xs, n, lane, &rows[G - 1], st, pm, tab, red, cfg.extra_mstep);
+    for (int G = 2; G <= GMAX; G++) fit_row<TW>(G, xs, n, lane, &rows[G - 1], st, pm, red, cfg.extra_mstep);
     T::sync();
     // near-tie diagnostic: two best BICs within 1e-9 relative
     bool bic_near = false;

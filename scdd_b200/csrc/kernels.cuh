@@ -302,10 +302,10 @@ __device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int
 
 template <int G>
 __device__ __noinline__ int label_of(const Row& r, double x) {
-    ParamsReg<G> p;
-    p.tab = EXP_TABLE_GLOBAL;
+    ParamsReg<G, true> p;
 #pragma unroll
     for (int k = 0; k < G; k++) { p.mu[k] = r.mu_em[k]; p.nh[k] = r.nh_em[k]; p.lc[k] = r.lc_em[k]; }
+    p.c0 = EXP_TAB_CONST[0]; p.c1 = EXP_TAB_CONST[1]; p.c2 = EXP_TAB_CONST[2];
     return map_label<G>(x, p);
 }
 
@@ -320,7 +320,7 @@ inline cudaError_t init_exp_table() {
 }
 constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
 constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
-constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/2048) table (16 KB)    // larger fit-sets are run by a whole CTA
+constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/2048) table (16 KB of static shared memory)    // larger fit-sets are run by a whole CTA
 
 // per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
@@ -338,10 +338,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tid = T::tid(lane);
-    double* tab = reinterpret_cast<double*>(smem_raw);            // 2^(j/2048), shared by the CTA
-    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) tab[i] = EXP_TABLE_GLOBAL[i];
+    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) EXP_TABLE_SH[i] = EXP_TABLE_GLOBAL[i];   // 2^(j/2048)
     __syncthreads();
-    unsigned char* region = smem_raw + FIT_TAB_BYTES + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
+    unsigned char* region = smem_raw + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
     Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
@@ -349,7 +348,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     double* xs = (TW > 1 && a.xs_global) ? a.xs_global + (size_t)blockIdx.x * a.np_max
                                          : reinterpret_cast<double*>(region + fit_region_head(TW));
     const bool lead0 = T::lead() && lane == 0;
-    if (lead0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lead0) { *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0}; store_consts(pm); }
     T::sync();
     const long long total = (long long)a.ngenes * a.nb * a.sets;
     const double NaN = nan("");
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             // which consumes RNG state mid-stream; reported, never silently fitted
             if (lead0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
         } else {
-            comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, tab, red);
+            comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, red);
             if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
         }
         if (lead0) {

@@ -315,7 +315,7 @@ struct Pipeline {
         if (warp_team) {
             const size_t per_warp = fit_smem_per_warp(np);
             int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
-            smem = per_warp * warps + FIT_TAB_BYTES;
+            smem = per_warp * warps;             // dynamic part; the exp table is static shared memory
             threads = warps * 32;
             grid = (int)std::min<long long>(n_sm, (total + warps - 1) / warps);
             CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -325,9 +325,9 @@ struct Pipeline {
             threads = FIT_CTA_WARPS * 32;
             grid = (int)std::min<long long>(n_sm, total);
             if (head + (size_t)np * sizeof(double) <= smem_cap) {
-                smem = head + (size_t)np * sizeof(double) + FIT_TAB_BYTES;
+                smem = head + (size_t)np * sizeof(double);
             } else {
-                smem = head + FIT_TAB_BYTES;
+                smem = head;
                 const size_t need = (size_t)grid * np;
                 if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
                 a.xs_global = d_xs_scratch.p;

@@ -7,19 +7,21 @@
 #include <cuda_runtime.h>
 #include "../../scdd_b200/csrc/kernels.cuh"
 using namespace scdd;
-__global__ void __launch_bounds__(512, 1) k(const double* src, const double* unsorted, int n, int np, int reps, double* out, double* counters, int gonly, int mode) {
+#ifndef WARPS
+#define WARPS 16
+#endif
+__global__ void __launch_bounds__(WARPS * 32, 1) k(const double* src, const double* unsorted, int n, int np, int reps, double* out, double* counters, int gonly, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* tab = reinterpret_cast<double*>(smem_raw);
-    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) tab[i] = EXP_TABLE_GLOBAL[i];
+    for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) EXP_TABLE_SH[i] = EXP_TABLE_GLOBAL[i];
     __syncthreads();
-    unsigned char* region = smem_raw + FIT_TAB_BYTES + warp * fit_smem_per_warp(np);
+    unsigned char* region = smem_raw + warp * fit_smem_per_warp(np);
     double* pm = reinterpret_cast<double*>(region);
     Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
     double* red = reinterpret_cast<double*>(st + 1);
     double* xs = reinterpret_cast<double*>(region + fit_region_head(1));
-    if (lane == 0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane == 0) { *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0}; store_consts(pm); }
     for (int j = lane; j < n; j += 32) xs[j] = src[j];
     __syncwarp();
     DevCfg cfg; cfg.alpha = 0.01; cfg.m0 = 0; cfg.s0 = 0.01; cfg.a0 = 0.01; cfg.b0 = 0.01; cfg.min_size = 3; cfg.restrict_ = 1; cfg.extra_mstep = 1;
@@ -31,18 +33,18 @@ __global__ void __launch_bounds__(512, 1) k(const double* src, const double* uns
             team_sort<1>(xs, np, lane);
         }
         if (mode >= 2) {
-            int comps = fit_set<1>(xs, n, lane, rows, cfg, st, pm, tab, red);
+            int comps = fit_set<1>(xs, n, lane, rows, cfg, st, pm, red);
             if (comps > 0) acc += joint_posterior(rows[comps - 1], comps, cfg);
         } else {
             for (int G = 2; G <= GMAX; G++) {
                 if (gonly && G != gonly) continue;
-                fit_row<1>(G, xs, n, lane, &rows[G - 1], st, pm, tab, red, 1);
+                fit_row<1>(G, xs, n, lane, &rows[G - 1], st, pm, red, 1);
             }
         }
         __syncwarp();
     }
-    if (lane == 1) out[blockIdx.x * 16 + warp] += acc;
-    if (lane == 0) { atomicAdd(&counters[0], st->triples); atomicAdd(&counters[1], st->em_iters); out[blockIdx.x * 16 + warp] = rows[4].bic; }
+    if (lane == 1) out[blockIdx.x * WARPS + warp] += acc;
+    if (lane == 0) { atomicAdd(&counters[0], st->triples); atomicAdd(&counters[1], st->em_iters); out[blockIdx.x * WARPS + warp] = rows[4].bic; }
 }
 int main() {
     init_exp_table();
@@ -50,9 +52,9 @@ int main() {
     std::mt19937 g(1); std::normal_distribution<double> nd(3.0, 1.0);
     std::vector<double> h(n); for (auto& v : h) v = nd(g); std::sort(h.begin(), h.end());
     double *d, *du, *out, *cnt; cudaMalloc(&d, n * 8); cudaMalloc(&du, n * 8);
-    { std::vector<double> hu = h; std::shuffle(hu.begin(), hu.end(), g); cudaMemcpy(du, hu.data(), n * 8, cudaMemcpyHostToDevice); } cudaMalloc(&out, 148 * 16 * 8); cudaMalloc(&cnt, 16);
+    { std::vector<double> hu = h; std::shuffle(hu.begin(), hu.end(), g); cudaMemcpy(du, hu.data(), n * 8, cudaMemcpyHostToDevice); } cudaMalloc(&out, 148 * WARPS * 8); cudaMalloc(&cnt, 16);
     cudaMemcpy(d, h.data(), n * 8, cudaMemcpyHostToDevice);
-    size_t smem = FIT_TAB_BYTES + 16 * fit_smem_per_warp(np);
+    size_t smem = WARPS * fit_smem_per_warp(np);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int cfgi = 0; cfgi < 7; cfgi++) {
         int gonly = cfgi < 5 ? (cfgi == 0 ? 0 : cfgi + 1) : 0, mode = cfgi < 5 ? 0 : cfgi - 4;
@@ -60,12 +62,12 @@ int main() {
         float best = 1e30f; double tr = 0, it = 0;
         for (int r = 0; r < 3; r++) {
             cudaMemset(cnt, 0, 16);
-            cudaEventRecord(a); k<<<148, 512, smem>>>(d, du, n, np, 20, out, cnt, gonly, mode); cudaEventRecord(b); cudaEventSynchronize(b);
+            cudaEventRecord(a); k<<<148, WARPS * 32, smem>>>(d, du, n, np, 20, out, cnt, gonly, mode); cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b); if (r && ms < best) best = ms;
             double c[2]; cudaMemcpy(c, cnt, 16, cudaMemcpyDeviceToHost); tr = c[0]; it = c[1];
         }
-        printf("mode %d G=%d%s: %.2f ms, %.3e triples/s, %.0f EM iterations (%.1f per fit), err=%s\n", mode, gonly, gonly ? "" : " (all)", best, tr / (best * 1e-3), it,
-               it / (148.0 * 16 * 20 * (gonly ? 1 : 4)), cudaGetErrorString(cudaGetLastError()));
+        printf("[W%d] mode %d G=%d%s: %.2f ms, %.3e triples/s, %.0f EM iterations (%.1f per fit), err=%s\n", WARPS, mode, gonly, gonly ? "" : " (all)", best, tr / (best * 1e-3), it,
+               it / (148.0 * WARPS * 20 * (gonly ? 1 : 4)), cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
