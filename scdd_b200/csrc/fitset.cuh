@@ -189,13 +189,11 @@ __device__ __forceinline__ double exp_table_sh(int D) {
 template <int G, bool GTAB = false>
 struct ParamsReg {
     double mu[G], nh[G], lc[G];
-    double c0, c1, c2;   // exp constants held in registers for the whole pass (load_consts)
     // 2^(j/2048): the CTA's shared copy, or (GTAB, label_of outside the fit loop) the global source
     __device__ __forceinline__ static double lookup(int D) { return GTAB ? EXP_TABLE_GLOBAL[D & expc::TMASK] : exp_table_sh(D); }
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
-    double c0, c1, c2;
     __device__ __forceinline__ static double lookup(int D) { return exp_table_sh(D); }
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
@@ -252,7 +250,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], prm.c0, MAGIC);                 // term_t
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);                 // term_t
 #pragma unroll
     for (int i = 0; i < N; i++) n[i] = SAT ? term_n(a[i], t[i]) : __double2loint(t[i]);
 #pragma unroll
@@ -260,9 +258,9 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], prm.c1, a[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(prm.c2, r[i], 0.5);                   // term_s
+    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], 0.5);                   // term_s
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
@@ -397,57 +395,32 @@ __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P&
 #endif
 // Loads the three exp constants once and hides their origin from the compiler, which otherwise re-loads them from
 // the constant bank inside every loop iteration (three extra issue slots per point).
-// The three exp constants.  Read from the constant bank the compiler re-loads them inside every loop iteration (three
-// issue slots per point); read from the pad slots of the team's shared parameter block (store_consts, once per
-// kernel) they cannot be re-materialised and stay in registers for the whole pass.
-#ifndef SCDD_PIN_CONSTS
-#define SCDD_PIN_CONSTS 0   // measured 1.9 % slower at 128 registers (the six extra registers cost more than three LDCs)
-#endif
-__device__ __forceinline__ void store_consts(double* pm) {
-    pm[3] = EXP_TAB_CONST[0]; pm[7] = EXP_TAB_CONST[1]; pm[11] = EXP_TAB_CONST[2];
-}
-template <class P>
-__device__ __forceinline__ void load_consts(P& p, const double* pm) {
-#if SCDD_PIN_CONSTS
-    p.c0 = pm[3]; p.c1 = pm[7]; p.c2 = pm[11];
-#else
-    p.c0 = EXP_TAB_CONST[0]; p.c1 = EXP_TAB_CONST[1]; p.c2 = EXP_TAB_CONST[2];
-#endif
-}
-
 template <int G>
 __device__ __forceinline__ auto load_params(const double* pm) {
 #if SCDD_PARAMS_SMEM
     if constexpr (G > SCDD_PARAMS_REG_MAXG) {
         ParamsSmem p;
         p.addr = (unsigned)__cvta_generic_to_shared(pm);
-        load_consts(p, pm);
         return p;
     } else {
         ParamsReg<G> p;
 #pragma unroll
         for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
-        load_consts(p, pm);
         return p;
     }
 #else
     ParamsReg<G> p;
 #pragma unroll
     for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
-    load_consts(p, pm);
     return p;
 #endif
 }
 
-#ifndef SCDD_SKEW
-#define SCDD_SKEW 0
-#endif
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            double (&v)[16]) {
     constexpr int NT = Team<TW>::NT;
     const auto prm = load_params<G>(pm);
-    typedef decltype(load_params<G>(pm)) P;
     double A[G], B[G], C[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
@@ -461,27 +434,6 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         // pointer-bumped loops: the load is [register + immediate] and the bound test compares addresses
         const double* px = xs + base + Team<TW>::tid(lane);
         const double* const pend = xs + stop;
-#if SCDD_SKEW
-        if (U == 1) {
-            // Software pipeline, two points in flight per thread: the front half of point i+1 (exp terms) is issued
-            // together with the back half of point i (reciprocal, normalisation, sums).  Ping-pong over two register
-            // sets to avoid moves.  Measured slower than the plain loop ("What did not help"): off by default.
-            if (px < pend) {
-                double e0[G], d0[G], q0[G], S0[1], e1[G], d1[G], q1[G], S1[1];
-                int M0[1], M1[1];
-                { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e0, d0, q0, S0, M0); }
-#pragma unroll 1
-                for (;;) {
-                    if (!(px < pend)) { accumulate_back<G, 1>(e0, d0, q0, S0, M0, A, B, C, pl, hs); break; }
-                    { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e1, d1, q1, S1, M1); }
-                    accumulate_back<G, 1>(e0, d0, q0, S0, M0, A, B, C, pl, hs);
-                    if (!(px < pend)) { accumulate_back<G, 1>(e1, d1, q1, S1, M1, A, B, C, pl, hs); break; }
-                    { double x[1] = {*px}; px += NT; estep_points<G, 1, SAT, P>(x, prm, e0, d0, q0, S0, M0); }
-                    accumulate_back<G, 1>(e1, d1, q1, S1, M1, A, B, C, pl, hs);
-                }
-            }
-        } else
-#endif
 #pragma unroll 1
         for (; px + NT * (U - 1) < pend; px += NT * U) {
             double x[U];

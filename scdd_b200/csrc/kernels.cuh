@@ -305,7 +305,6 @@ __device__ __noinline__ int label_of(const Row& r, double x) {
     ParamsReg<G, true> p;
 #pragma unroll
     for (int k = 0; k < G; k++) { p.mu[k] = r.mu_em[k]; p.nh[k] = r.nh_em[k]; p.lc[k] = r.lc_em[k]; }
-    p.c0 = EXP_TAB_CONST[0]; p.c1 = EXP_TAB_CONST[1]; p.c2 = EXP_TAB_CONST[2];
     return map_label<G>(x, p);
 }
 
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     double* xs = (TW > 1 && a.xs_global) ? a.xs_global + (size_t)blockIdx.x * a.np_max
                                          : reinterpret_cast<double*>(region + fit_region_head(TW));
     const bool lead0 = T::lead() && lane == 0;
-    if (lead0) { *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0}; store_consts(pm); }
+    if (lead0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
     T::sync();
     const long long total = (long long)a.ngenes * a.nb * a.sets;
     const double NaN = nan("");

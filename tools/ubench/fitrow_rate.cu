@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k(const double* src, const doub
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
     double* red = reinterpret_cast<double*>(st + 1);
     double* xs = reinterpret_cast<double*>(region + fit_region_head(1));
-    if (lane == 0) { *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0}; store_consts(pm); }
+    if (lane == 0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int j = lane; j < n; j += 32) xs[j] = src[j];
     __syncwarp();
     DevCfg cfg; cfg.alpha = 0.01; cfg.m0 = 0; cfg.s0 = 0.01; cfg.a0 = 0.01; cfg.b0 = 0.01; cfg.min_size = 3; cfg.restrict_ = 1; cfg.extra_mstep = 1;
