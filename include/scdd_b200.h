@@ -182,6 +182,9 @@ int32_t scdd_plan_run_chunk(scdd_plan* plan, void* cuda_stream, int32_t nperms);
 void* scdd_plan_bf_device_ptr(scdd_plan* plan);
 /* synchronises the device and reads the counters accumulated since plan creation */
 int32_t scdd_plan_stats(scdd_plan* plan, scdd_stats* stats);
+/* EM work per resident gene (point x component x iteration triples) measured on the plan's first chunk -- what the
+ * library orders its own work by; exposed so that a multi-GPU host can balance its gene shards by measured cost. */
+int32_t scdd_plan_gene_costs(scdd_plan* plan, double* cost /* [ngenes] */);
 void scdd_plan_destroy(scdd_plan* plan);
 
 /* ---- host-side self checks (no GPU needed) ---- */

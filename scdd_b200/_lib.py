@@ -56,7 +56,7 @@ FIT_DTYPE = np.dtype([("G", np.int32), ("model_v", np.int32), ("n", np.int32), (
 EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set_devices", "scdd_default_cfg",
            "scdd_fit_observed", "scdd_perm_bf", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
-           "scdd_plan_stats", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax",
+           "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax",
            "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
 
 
@@ -91,6 +91,7 @@ def lib():
     L.scdd_plan_bf_device_ptr.argtypes = [vp]
     L.scdd_plan_bf_device_ptr.restype = vp
     L.scdd_plan_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.scdd_plan_gene_costs.argtypes = [vp, vp]
     L.scdd_plan_destroy.argtypes = [vp]
     L.scdd_plan_destroy.restype = None
     L.scdd_selftest_x87_cumsum.argtypes = [vp, C.c_int32, vp]

@@ -1206,6 +1206,18 @@ int32_t scdd_plan_stats(scdd_plan* plan, scdd_stats* stats) {
     });
 }
 
+int32_t scdd_plan_gene_costs(scdd_plan* plan, double* cost) {
+    if (!plan || !cost) return fail(SCDD_ERR_BAD_ARG, "null");
+    if (!plan->P.have_order || plan->P.d_gene_cost.n < (size_t)plan->P.ngenes)
+        return fail(SCDD_ERR_BAD_ARG, "no chunk has been measured yet (run one chunk first; blocks with fewer genes than 2 x SMs are not measured)");
+    return guarded([&]() -> int {
+        CK(cudaSetDevice(plan->P.device));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(cost, plan->P.d_gene_cost.p, (size_t)plan->P.ngenes * sizeof(double), cudaMemcpyDeviceToHost));
+        return SCDD_OK;
+    });
+}
+
 void scdd_plan_destroy(scdd_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->P.device);

@@ -246,6 +246,12 @@ class Plan:
         _lib.check(_lib.lib().scdd_plan_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def gene_costs(self):
+        """EM work per gene measured on the first chunk (scdd_plan_gene_costs)."""
+        out = np.zeros(self.ngenes)
+        _lib.check(_lib.lib().scdd_plan_gene_costs(self._h, out.ctypes.data))
+        return out
+
     def close(self):
         if self._h:
             _lib.lib().scdd_plan_destroy(self._h)

@@ -84,3 +84,19 @@ def test_oracle_sample_of_the_benchmark_workload(workload):
     out, _ = hp.perm_bf(ly, cc, oo, 2, seed6=seeds, cfg=hp.make_cfg(**PRIORS))
     ref = po.perm_batch(ly, cc, oo, 2, seed6=seeds, cfg=po.make_cfg(**PRIORS))
     np.testing.assert_allclose(out, ref, rtol=1e-8)
+
+
+def test_plan_gene_costs_account_for_the_measured_chunk():
+    """scdd_plan_gene_costs: the per-gene EM work the library orders its launches by sums to the chunk's triples"""
+    from scdd_b200.simulate import simulate_set_style
+    X, cond = simulate_set_style(400, 100, seed=5)
+    logy, c01, off = hp.gene_csr(X, cond)
+    plan = hp.Plan(0, logy, c01, off, 4, hp.gene_seeds(3, 400), cfg=hp.make_cfg(alpha=0.01))
+    with pytest.raises(hp.ScddError, match="no chunk has been measured"):
+        plan.gene_costs()
+    plan.run_chunk(0, 4)
+    st = plan.stats()
+    cost = plan.gene_costs()
+    assert cost.shape == (400,) and (cost > 0).all()
+    np.testing.assert_allclose(cost.sum(), st["triples"], rtol=1e-12)
+    plan.close()

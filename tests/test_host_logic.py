@@ -142,6 +142,20 @@ def test_shards_partition_the_genes():
         assert max(len(r) for r in rows) - min(len(r) for r in rows) <= 1
 
 
+def test_cost_balanced_shards_partition_and_balance():
+    rng = np.random.default_rng(3)
+    cost = rng.lognormal(0.0, 1.2, 20000)           # heavy-tailed, like EM work per gene
+    for world in (2, 8):
+        parts = bench.balance_rows(cost, world)
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(20000))
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() / loads.mean() < 1.001     # interleaving the same costs is off by several percent
+        inter = np.array([cost[bench.shard_rows(20000, r, world)].sum() for r in range(world)])
+        assert loads.max() <= inter.max()
+        again = bench.balance_rows(cost, world)
+        assert all(np.array_equal(a, b) for a, b in zip(parts, again))   # deterministic: every rank computes the same split
+
+
 _GLOO = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["SCDD_ROOT"])
