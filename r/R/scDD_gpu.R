@@ -41,7 +41,8 @@ genefit_gpu <- function(dat, condition, ref, prior, min.size, with.bf = TRUE) {
     c1[[j]] <- mk(3 * j - 1, r$class.c[s][c0])
     c2[[j]] <- mk(3 * j, r$class.c[s][!c0])
   }
-  list(oa = oa, c1 = c1, c2 = c2, bf = r$bf, den = r$den)
+  # raw / csr: the flat class vectors and the CSR block, for feDP_gpu(), zhat_gpu() and luOutlier_gpu()
+  list(oa = oa, c1 = c1, c2 = c2, bf = r$bf, den = r$den, raw = r, csr = g)
 }
 
 # replaces:  bf.perm <- bplapply(..., permMclustGene(...))   R/scDD.R:458-463  (and :420-455)
