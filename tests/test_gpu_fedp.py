@@ -118,3 +118,34 @@ def test_scdd_categories_through_the_api(golden_dir):
     padj = G["nonzero.pvalue.adj"]
     assert all(c is None for c, p in zip(cats, padj) if p < 0.05)          # significant -> classifyDD (R)
     assert set(c for c in cats if c is not None) <= {"NS", "DP", "NC"}
+
+
+def test_scdd_with_filtered_and_constant_genes():
+    """genes below min.nonzero and genes with constant nonzero values are skipped (R/scDD.R:270-310): NA rows in the
+    Genes table, default 0/1 entries in the Zhat matrices, and the fitted genes unaffected by their presence"""
+    rng = np.random.default_rng(21)
+    ng, nc = 24, 80
+    cond = np.repeat(["A", "B"], nc // 2)
+    X = np.exp(rng.normal(2.0, 0.6, (ng, nc)))
+    X[rng.random(X.shape) < 0.2] = 0
+    X[3, :] = 0
+    X[3, :2] = 5.0                                   # two nonzero cells in one condition only: not fitted
+    X[10, :] = np.where(X[10] > 0, 7.0, 0.0)         # constant nonzero values: skipped
+    X = np.asfortranarray(X)                         # an R-style (column-major) matrix goes through unchanged
+    pri = dict(alpha=0.01, mu0=0, s0=0.01, a0=0.01, b0=0.01)
+    out = api.scDD(api.SingleCellExperiment({"normcounts": X}, {"condition": cond}), prior_param=pri, permutations=8,
+                   testZeroes=False, param={"RNGseed": 3}, verbose=False)
+    G = api.results(out, "Genes")
+    tofit = out.metadata["_scdd_b200"]["tofit"]
+    assert 3 not in tofit and 10 not in tofit and tofit.size == ng - 2
+    for g in (3, 10):
+        assert np.isnan(G["nonzero.pvalue"][g]) and np.isnan(G["Clusters.combined"][g]) and G["DDcategory"][g] is None
+    Z = api.results(out, "Zhat.combined")
+    assert np.array_equal(Z[3], (X[3] != 0).astype(float)) and np.array_equal(Z[10], (X[10] != 0).astype(float))
+    assert np.array_equal(Z == 0, X == 0)
+    # the same genes alone give the same p-values: streams are assigned by position among the fitted genes
+    keep = np.setdiff1d(np.arange(ng), [3, 10])
+    out2 = api.scDD(api.SingleCellExperiment({"normcounts": np.ascontiguousarray(X[keep])}, {"condition": cond}),
+                    prior_param=pri, permutations=8, testZeroes=False, param={"RNGseed": 3}, verbose=False)
+    assert np.array_equal(api.results(out2, "Genes")["nonzero.pvalue"], G["nonzero.pvalue"][keep])
+    assert np.array_equal(api.results(out2, "Zhat.c1"), api.results(out, "Zhat.c1")[keep])
