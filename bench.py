@@ -236,7 +236,7 @@ def main():
     # ---------------- resident arm: `value`
     plan = hp.Plan(local, logy, c01, off, nperm, seeds, cfg=cfg)
     stream = torch.cuda.current_stream().cuda_stream
-    shard_note = "interleaved"
+    shard_note = "interleaved" if world > 1 else "all genes on the one GPU"
     if world > 1 and not args.no_balance:
         # Untimed set-up: EM work per gene is a property of the gene, so one measured chunk on the interleaved shards
         # lets all ranks re-partition the genes longest-first by MEASURED cost (the library orders its own work the
