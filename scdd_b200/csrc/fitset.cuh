@@ -26,6 +26,7 @@ constexpr double PI2LOG = 1.837877066409345;   // log(2*pi), mclust.f
 constexpr double SMALOG = -708.0;              // mclust.f: exp() arguments below this give z = 0
 constexpr int NQCAP = 64;                      // qclass: give up growing the quantile grid beyond this
 constexpr int EM_ITER_CAP = 100000;            // safety cap (mclust: itmax = .Machine$integer.max)
+constexpr int FIT_DEFERRED = -2;               // fit_set: stopped by the caller's iteration budget
 
 struct DevCfg {
     double alpha, m0, s0, a0, b0;
@@ -534,16 +535,16 @@ __device__ __noinline__ double label_dispatch(int G, const double* xs, int n, in
 // One copy of this code serves every G: the scalar M-step runs once per warp with lane k owning
 // component k (lanes >= G shadow component 0), only the point loops are specialised on G.
 // ---------------------------------------------------------------------------------------------
-template <int TW>
-__device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
-                                     double* pm, double* red, int extra_mstep) {
+template <int TW, bool BUDGET>
+__device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
+                                     double* pm, double* red, int extra_mstep, int iter_cap) {
     typedef Team<TW> T;
     const double eps = DBL_EPSILON, rteps = 1.4901161193847656e-08, tol = 1e-5;
     const double dn = (double)n;
     const int tid = T::tid(lane);
     const bool lead0 = T::lead() && lane == 0;
     if (lead0) { row->valid = 0; row->iters = 0; }
-    if (G > n) return;   // mclustBIC: G <- G[G <= n]
+    if (G > n) return false;   // mclustBIC: G <- G[G <= n]
     const int kown = lane < G ? lane : 0;
     const bool owner = lane < G;
     const double range2 = (xs[n - 1] - xs[0]) * (xs[n - 1] - xs[0]);   // xs is sorted: every |x - mu_k| <= range
@@ -569,7 +570,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         }
         double t = T::reduce(v, lane, red);
         double cnt = slot(t, kown), sx = slot(t, GMAX + kown);
-        if (__any_sync(FULLMASK, owner && cnt <= rteps)) return;   // an empty class: "mixing proportion fell below threshold"
+        if (__any_sync(FULLMASK, owner && cnt <= rteps)) return false;   // an empty class: "mixing proportion fell below threshold"
         mu_own = sx / cnt;
         pro_own = cnt / dn;
         double m0 = __shfl_sync(FULLMASK, mu_own, 0), m1 = __shfl_sync(FULLMASK, mu_own, 1);
@@ -619,7 +620,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         hold = hood;
         if (fabs(diff - bound) <= 1e-7 * bound) near_tol = true;
         if (!(diff > bound)) break;
-        if (iter >= EM_ITER_CAP) { capped = true; break; }
+        if (iter >= (BUDGET ? iter_cap : EM_ITER_CAP)) { capped = true; break; }
         // ---- M-step (lane k: component k) ----
         if (__any_sync(FULLMASK, owner && A <= rteps)) { failed = true; break; }
         const double ra = fast_rcp(A);
@@ -628,6 +629,9 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         sig_own = fma(-dm, dm, C * ra);
         pro_own = A * inv_n;
     }
+    // stopped by the caller's iteration budget (not by the safety cap): nothing is recorded, the caller re-runs the
+    // whole fit-set elsewhere (fit_kernel, "deferred" items)
+    if (BUDGET && capped && iter_cap < EM_ITER_CAP) return true;
     if (lead0) {
         // work counters (per team, shared memory): iterations executed, points x components, points
         st->em_iters += (double)iter;
@@ -637,7 +641,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         if (capped) st->cap_hits += 1.0;
         row->iters = iter;
     }
-    if (failed) return;
+    if (failed) return false;
 
     // ---- converged: BIC, parameters, labels ----
     double mean_out = mu_own, sig_out = sig_own;
@@ -674,6 +678,7 @@ __device__ __noinline__ void fit_row(int G, const double* xs, int n, int lane, R
         row->bic = 2.0 * hood - (double)(3 * G - 1) * log(dn);
         row->valid = 1;
     }
+    return false;
 }
 
 // G = 1 row: mvn1d closed form
@@ -929,14 +934,17 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
 }
 
 // ---------------------------------------------------------------------------------------------
-// The whole fit-set on a sorted slab.  Returns the selected number of components (0 = failed).
+// The whole fit-set on a sorted slab.  Returns the selected number of components (0 = failed), or FIT_DEFERRED when
+// an EM needed more than iter_cap (< EM_ITER_CAP) iterations: nothing has been recorded and the caller re-runs the
+// fit-set with a wider team.
 // ---------------------------------------------------------------------------------------------
-template <int TW>
+template <int TW, bool BUDGET = false>
 __device__ __forceinline__ int fit_set(const double* xs, int n, int lane, Row* rows, const DevCfg& cfg, WarpStats* st,
-                                       double* pm, double* red) {
+                                       double* pm, double* red, int iter_cap = EM_ITER_CAP) {
     typedef Team<TW> T;
     fit_row1<TW>(xs, n, lane, &rows[0], red);
-    for (int G = 2; G <= GMAX; G++) fit_row<TW>(G, xs, n, lane, &rows[G - 1], st, pm, red, cfg.extra_mstep);
+    for (int G = 2; G <= GMAX; G++)
+        if (fit_row<TW, BUDGET>(G, xs, n, lane, &rows[G - 1], st, pm, red, cfg.extra_mstep, iter_cap)) return FIT_DEFERRED;
     T::sync();
     // near-tie diagnostic: two best BICs within 1e-9 relative
     bool bic_near = false;

@@ -290,6 +290,12 @@ struct FitArgs {
     DevCfg cfg;
     unsigned long long* work_counter;
     double* stats;             // [9] global accumulators (WarpStats order)
+    // Two-pass launches (observed fits): pass 1 runs warp teams with an EM iteration budget and marks the fit-sets that
+    // exceed it; pass 2 (only_deferred) re-runs just those with one CTA per fit-set.  A launch is otherwise as long as
+    // its slowest fit-set on ONE warp (thousands of EM iterations for ~1 % of the observed fit-sets).
+    int iter_budget;           // 0 = none
+    int only_deferred;
+    unsigned char* deferred;   // [ngenes * nb * sets], nullable
 };
 
 __device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int n, int b, uint32_t i) {
@@ -331,7 +337,9 @@ __host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
 }
 static_assert(fit_region_head(1) % 16 == 0 && fit_region_head(FIT_CTA_WARPS) % 16 == 0, "xs must stay 16-byte aligned");
 
-template <int TW>
+// BUDGET: pass 1 of a two-pass launch (see FitArgs::iter_budget).  A separate instantiation, so that the kernel of the
+// permutation chunks is compiled exactly as if the budget logic did not exist.
+template <int TW, bool BUDGET = false>
 __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     typedef Team<TW> T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -365,6 +373,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             __syncthreads();
         }
         if (item >= total) break;
+        if (a.only_deferred && !a.deferred[item]) continue;
         const int w = (int)(item % a.sets);
         const long long u = item / a.sets;
         const int b = (int)(u % a.nb);
@@ -402,7 +411,18 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             // which consumes RNG state mid-stream; reported, never silently fitted
             if (lead0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
         } else {
-            comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, red);
+            if (BUDGET) {
+                WarpStats snap;
+                if (lead0) snap = *st;
+                comps = fit_set<TW, true>(xs, n, lane, rows, a.cfg, st, pm, red, a.iter_budget);
+                if (comps == FIT_DEFERRED) {   // team-uniform
+                    if (lead0) { *st = snap; a.deferred[item] = 1; }
+                    T::sync();
+                    continue;
+                }
+            } else {
+                comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, red);
+            }
             if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
         }
         if (lead0) {

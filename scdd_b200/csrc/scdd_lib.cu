@@ -298,7 +298,7 @@ struct Pipeline {
 
     // launches the persistent fit kernel over ngenes x nb x sets fit-sets
     DevBuf<double> d_xs_scratch;
-    void launch_fit(cudaStream_t s, FitArgs a, int nmax_points) {
+    void launch_fit(cudaStream_t s, FitArgs a, int nmax_points, bool force_cta = false) {
         int np = 2;
         while (np < nmax_points) np <<= 1;
         const long long total = (long long)a.ngenes * a.nb * a.sets;
@@ -311,14 +311,15 @@ struct Pipeline {
         a.xs_global = nullptr;
         int grid, threads;
         size_t smem;
-        const bool warp_team = nmax_points <= FIT_WARP_TEAM_MAX_POINTS;
+        const bool warp_team = nmax_points <= FIT_WARP_TEAM_MAX_POINTS && !force_cta;
         if (warp_team) {
             const size_t per_warp = fit_smem_per_warp(np);
             int warps = (int)std::min<size_t>(FIT_MAX_WARPS, smem_cap / per_warp);
             smem = per_warp * warps;             // dynamic part; the exp table is static shared memory
             threads = warps * 32;
             grid = (int)std::min<long long>(n_sm, (total + warps - 1) / warps);
-            CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (a.iter_budget) CK(cudaFuncSetAttribute(fit_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         } else {
             // one CTA per fit-set; the vector stays in shared memory when it fits, else in an L2-resident slab
             const size_t head = fit_region_head(FIT_CTA_WARPS);
@@ -337,7 +338,8 @@ struct Pipeline {
         CK(cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), s));
         Timed t;
         if (time_kernels) t = tick_begin(0, s);
-        if (warp_team) fit_kernel<1><<<grid, threads, smem, s>>>(a);
+        if (warp_team && a.iter_budget) fit_kernel<1, true><<<grid, threads, smem, s>>>(a);
+        else if (warp_team) fit_kernel<1><<<grid, threads, smem, s>>>(a);
         else fit_kernel<FIT_CTA_WARPS><<<grid, threads, smem, s>>>(a);
         CK(cudaGetLastError());
         if (time_kernels) tick_end(t, s);
@@ -365,6 +367,7 @@ struct Pipeline {
         a.ngenes = ngenes;
         a.gene_order = have_order ? d_gene_order.p : nullptr;
         a.gene_cost = nullptr;
+        a.iter_budget = 0; a.only_deferred = 0; a.deferred = nullptr;
         return a;
     }
 
@@ -552,6 +555,9 @@ void scdd_default_cfg(scdd_cfg* c) {
 }
 
 // ---------------------------------------------------------------- observed fits
+// EM iterations one warp spends on a single mixture before the fit-set is handed to a CTA (observed fits)
+static const int OBSERVED_ITER_BUDGET = 500;
+
 static void fit_observed_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng,
                              const scdd_cfg* cfg, scdd_fit* fits, int32_t* cls_oa, int32_t* cls_c,
                              double* bf, double* den, scdd_stats* st) {
@@ -581,7 +587,21 @@ static void fit_observed_one(int dev, const double* logy, const int64_t* off, co
         FitArgs a = P.base_args();
         a.nb = 1; a.sets = 3; a.jp = P.d_jp.p;
         a.fits = d_fits.p; a.cls_oa = d_oa.p; a.cls_c = d_c.p;
-        P.launch_fit(s, a, P.max_n);
+        if (P.max_n <= FIT_WARP_TEAM_MAX_POINTS) {
+            // pass 1: one warp per fit-set with an EM iteration budget; pass 2: the ~1 % of fit-sets that exceeded it,
+            // one CTA each (a launch would otherwise last as long as its slowest fit-set on a single warp)
+            DevBuf<unsigned char> d_deferred;
+            d_deferred.alloc(3 * (size_t)ng);
+            CK(cudaMemsetAsync(d_deferred.p, 0, 3 * (size_t)ng, s));
+            a.deferred = d_deferred.p;
+            a.iter_budget = OBSERVED_ITER_BUDGET;
+            P.launch_fit(s, a, P.max_n);
+            a.iter_budget = 0; a.only_deferred = 1;
+            P.launch_fit(s, a, P.max_n, /*force_cta=*/true);
+            CK(cudaStreamSynchronize(s));   // d_deferred goes out of scope
+        } else {
+            P.launch_fit(s, a, P.max_n);
+        }
         std::vector<double> jp(3 * (size_t)ng);
         const int64_t base = off[0];
         CK(cudaMemcpyAsync(fits, d_fits.p, 3 * (size_t)ng * sizeof(scdd_fit), cudaMemcpyDeviceToHost, s));

@@ -20,14 +20,17 @@ def workload():
 
 
 def test_identity_permutation_reproduces_observed_bf(workload):
-    """permMclustGene with the identity permutation is genefit's numerator: same fits, same bits"""
+    """permMclustGene with the identity permutation is genefit's numerator: same fits -- and the same bits wherever the
+    observed fit-set ran on a warp like the permuted one; the ~1 % of observed fit-sets that exceed the EM iteration
+    budget are re-run by a CTA team (another summation order) and agree to rounding"""
     X, cond, logy, c01, off = workload
     ng = 4000
     o = off[:ng + 1]
     ident = np.concatenate([np.arange(1, int(o[g + 1] - o[g]) + 1, dtype=np.int32) for g in range(ng)])
     out, st = hp.perm_bf(logy, c01, o, 1, perm_idx=ident, cfg=hp.make_cfg(**PRIORS))
     _, _, _, bf, den, _ = hp.fit_observed(logy, c01, o, cfg=hp.make_cfg(**PRIORS))
-    assert np.array_equal(out[:, 0], bf)
+    np.testing.assert_allclose(out[:, 0], bf, rtol=1e-11)
+    assert (out[:, 0] == bf).mean() > 0.9
     assert np.isfinite(bf).all() and np.isfinite(den).all()
 
 

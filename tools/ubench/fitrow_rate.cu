@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k(const double* src, const doub
         } else {
             for (int G = 2; G <= GMAX; G++) {
                 if (gonly && G != gonly) continue;
-                fit_row<1>(G, xs, n, lane, &rows[G - 1], st, pm, red, 1);
+                fit_row<1, false>(G, xs, n, lane, &rows[G - 1], st, pm, red, 1, EM_ITER_CAP);
             }
         }
         __syncwarp();
