@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define SCDD_GMAX 5          /* Mclust(G = 1:5), R/mclust.restricted.R:52 */
-#define SCDD_ABI_VERSION 1
+#define SCDD_ABI_VERSION 2
 
 enum {
     SCDD_OK = 0,
@@ -36,7 +36,8 @@ enum {
     SCDD_ERR_BAD_ARG = -2,
     SCDD_ERR_CUDA = -3,
     SCDD_ERR_TOO_LARGE = -4,   /* a fit-set has more points than the kernels support */
-    SCDD_ERR_FIT_FAILED = -5   /* some fit-set had no valid model (all BIC NA) -- outputs hold NaN there */
+    SCDD_ERR_FIT_FAILED = -5,  /* some fit-set had no valid model (all BIC NA) -- outputs hold NaN there */
+    SCDD_ERR_INTERRUPTED = -6  /* the caller's interrupt hook asked to stop between two permutation chunks */
 };
 
 /* prior_param + the arguments of scDD() that reach the hot path (R/scDD.R:217-225, :245-249) */
@@ -67,7 +68,8 @@ typedef struct {
     double iter_cap_hits;  /* EM fits stopped by the safety cap instead of the tolerance (expected 0) */
     double tol_near;       /* EM fits whose stopping test was within 1e-7 (relative) of the tolerance */
     double bic_near;       /* fit-sets whose two best BICs differ by < 1e-9 relative (near ties) */
-    double const_sets;     /* fit-sets with all values identical (reference would jitter with runif) */
+    double const_sets;     /* fit-sets with all values identical: jittered from the gene's stream as the reference does
+                              (device-drawn permutations), or failed (no stream: observed data, perm_idx) */
     double failed_sets;    /* fit-sets with no valid model */
     double fit_kernel_ms;  /* device time of the mixture-fit kernel(s), CUDA events */
     double fit_kernel_launches;
@@ -104,10 +106,41 @@ int32_t scdd_fit_observed(const double* logy, const int64_t* gene_off, const int
  *              (R_unif_index rejection sampling); seed6_out (nullable) receives the advanced states.
  * cdr != NULL selects adjust.perms=TRUE (R/permutations.R:230-267): cdr[nnz] is the cellular
  * detection rate C of each nonzero cell; residuals of lm(y ~ C) are permuted and oa is refitted,
- * bf_perm = JP(c1)+JP(c2)-JP(oa). */
+ * bf_perm = JP(c1)+JP(c2)-JP(oa).
+ * Constant subsets (R/mclust.restricted.R:48-50): with seed6 a permuted subset whose values are all identical gets
+ * the reference's runif(n, -0.1, 0.1) jitter, drawn from the gene's stream at the position R draws it (between this
+ * permutation's sample() and the next); stats->const_sets counts them.  With perm_idx no stream exists: such a
+ * fit-set yields NaN and SCDD_ERR_FIT_FAILED.
+ * With several devices (scdd_set_devices) the genes are sharded: 8 permutations on shards balanced by cell counts
+ * measure the EM work per gene, the rest runs on shards re-dealt by that measured cost. */
 int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
                      int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
                      const scdd_cfg* cfg, double* bf_perm, uint32_t* seed6_out, scdd_stats* stats);
+
+/* Options of scdd_perm_bf_ex (all-zero = scdd_perm_bf).
+ *   seed_mode 0: seed6 is [ngenes*6], one stream per gene = parallelBy "Genes" (bplapply over genes, R/scDD.R:458).
+ *   seed_mode 1: seed6 is [B*6], permutation b of EVERY gene is drawn from the start of stream b = parallelBy
+ *                "Permutations": scDD() loops over the genes in the master and permMclust / permMclustCov run
+ *                bplapply(1:nperms, ...) under the same RNGseed for each of them (R/scDD.R:414-455,
+ *                R/permutations.R:177, :99).  seed6_out is not written.
+ *   jp_terms   : (nullable) [ngenes*B*sets], sets = 2 (3 with cdr): the jointPosterior terms JP(c1), JP(c2)[, JP(oa)]
+ *                of every gene-permutation, whose combination is bf_perm (R/permutations.R:265-267, :281-282).
+ *   interrupt  : (nullable) polled on the calling thread between chunks of <= 16 permutations; a non-zero return stops
+ *                the call with SCDD_ERR_INTERRUPTED.  The R glue passes a hook that runs R_CheckUserInterrupt() under
+ *                R_ToplevelExec(), so that a 60 s permutation job stays interruptible. */
+typedef struct {
+    int32_t seed_mode;
+    int32_t reserved;
+    double* jp_terms;
+    int32_t (*interrupt)(void* arg);
+    void* interrupt_arg;
+} scdd_perm_opts;
+int32_t scdd_perm_bf_ex(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                        int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                        const scdd_cfg* cfg, const scdd_perm_opts* opts, double* bf_perm, uint32_t* seed6_out,
+                        scdd_stats* stats);
+/* frees the per-device buffers (HBM blocks, pinned staging, streams) that scdd_perm_bf keeps between calls */
+void scdd_release_cache(void);
 
 /* ---- KS test:  testKS / onegene, R/Test_KS.R:55-65  (stats::ks.test(x1, x2, exact=FALSE)) ----
  * vals[nnz]: the values to compare per gene (raw counts; zeros already dropped unless inclZero),

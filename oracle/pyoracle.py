@@ -73,6 +73,9 @@ def lib():
         L.orc_genefit_batch.argtypes = [dp, ip, lp, C.c_int32, C.POINTER(Cfg), C.POINTER(Fit), ip, ip, dp, dp, C.c_int32]
         L.orc_perm_batch.argtypes = [dp, ip, lp, C.c_int32, C.c_int32, ip, up, C.POINTER(Cfg), dp, C.c_int32]
         L.orc_perm_batch_cov.argtypes = [dp, ip, dp, lp, C.c_int32, C.c_int32, ip, up, C.POINTER(Cfg), dp, C.c_int32]
+        L.orc_perm_batch_ex.argtypes = [dp, ip, dp, lp, C.c_int32, C.c_int32, ip, up, C.c_int32, C.POINTER(Cfg), dp,
+                                        C.c_int32, lp, dp]
+        L.orc_mclust_restricted_rng.argtypes = [dp, C.c_int32, C.POINTER(Cfg), C.POINTER(Fit), ip, C.POINTER(Rng), ip]
         L.orc_ks_batch.argtypes = [dp, ip, lp, C.c_int32, C.c_int32, dp, dp, C.c_int32]
         L.orc_last_work.argtypes = [dp, dp]
     return _LIB
@@ -260,6 +263,50 @@ def perm_batch(logy, cond, gene_off, B, perm_idx=None, seed6=None, cfg=None, nth
     if rc != 0:
         raise RuntimeError("oracle permutation fit failed")
     return out
+
+
+def perm_batch_ex(logy, cond, gene_off, B, perm_idx=None, seed6=None, seed_mode=0, cfg=None, nthreads=0, cdr=None,
+                  allow_failed=True):
+    """Both permutation drivers with every option (orc_perm_batch_ex): returns dict(bf_perm[ngenes, B],
+    jp_terms[ngenes, B, sets] = JP(c1), JP(c2)[, JP(oa)], n_jittered, rc).
+    seed_mode 1 = parallelBy "Permutations" streams (seed6 is [B, 6])."""
+    cfg = cfg or make_cfg()
+    logy = np.ascontiguousarray(logy, dtype=np.float64)
+    cond = np.ascontiguousarray(cond, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    ng = gene_off.size - 1
+    sets = 3 if cdr is not None else 2
+    out = np.zeros((ng, B))
+    terms = np.zeros((ng, B, sets))
+    pi = sd = cd = None
+    if perm_idx is not None:
+        perm_idx = np.ascontiguousarray(perm_idx, dtype=np.int32)
+        pi = _i(perm_idx)
+    if seed6 is not None:
+        seed6 = np.ascontiguousarray(seed6, dtype=np.uint32)
+        assert seed6.size == 6 * (B if seed_mode else ng)
+        sd = _u(seed6)
+    if cdr is not None:
+        cdr = np.ascontiguousarray(cdr, dtype=np.float64)
+        cd = _d(cdr)
+    nj = C.c_int64(0)
+    rc = lib().orc_perm_batch_ex(_d(logy), _i(cond), cd, _l(gene_off), ng, B, pi, sd, int(seed_mode), C.byref(cfg),
+                                 _d(out), nthreads, C.cast(C.byref(nj), C.POINTER(C.c_int64)), _d(terms))
+    if rc != 0 and not allow_failed:
+        raise RuntimeError("oracle permutation fit failed")
+    return dict(bf_perm=out, jp_terms=terms, n_jittered=int(nj.value), rc=rc)
+
+
+def mclust_restricted_rng(y, rng, min_size=3, cfg=None):
+    """mclustRestricted under a live stream (jitter of R/mclust.restricted.R:48-50): returns (fit dict or None, jittered)."""
+    cfg = cfg or make_cfg(min_size=min_size)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    f = Fit()
+    cls = np.zeros(y.size, dtype=np.int32)
+    j = C.c_int32(0)
+    rc = lib().orc_mclust_restricted_rng(_d(y), y.size, C.byref(cfg), C.byref(f), _i(cls), C.byref(rng.r),
+                                         C.cast(C.byref(j), C.POINTER(C.c_int32)))
+    return (None if rc != 0 else _fit_dict(f, cls)), bool(j.value)
 
 
 def ks_batch(vals, cond, gene_off, old_pvalue=False, nthreads=0):

@@ -376,10 +376,49 @@ static double vmin(const double* v, int n) {
     return m;
 }
 
+/* R/mclust.restricted.R:48-50: `if (length(unique(y))==1) y <- y + runif(length(y), -0.1, 0.1)`.
+   runif(n, a, b) is `a + (b - a) * unif_rand()` per element (nmath/runif.c), drawn in element order from the
+   stream that is current when mclustRestricted runs -- inside bplapply that is the element's own L'Ecuyer stream,
+   so the draw sits mid-stream between two sample() calls of permMclustGene.  Returns 1 if the jitter was applied. */
+int orc_jitter_if_constant(double* y, int32_t n, orc_rng* rng) {
+    if (n < 1) return 0;                       /* length(unique(numeric(0))) == 0 */
+    for (int i = 1; i < n; i++) if (y[i] != y[0]) return 0;
+    const double a = -0.1, b = 0.1;
+    for (int i = 0; i < n; i++) {
+        double u = orc_unif_rand(rng);
+        double w = (b - a) * u;
+        y[i] = y[i] + (a + w);
+    }
+    return 1;
+}
+
+static int mclust_restricted_core(const double* y_in, int32_t n, const orc_cfg* cfg, orc_fit* out, int32_t* cls);
+
+/* mclustRestricted with the caller's RNG: the jittered copy is local to the function, as in R (the caller's y, which
+   jointPosterior receives afterwards, keeps the identical values -- R/permutations.R:278-282). */
+int orc_mclust_restricted_rng(const double* y_in, int32_t n, const orc_cfg* cfg, orc_fit* out, int32_t* cls,
+                              orc_rng* rng, int32_t* jittered) {
+    if (jittered) *jittered = 0;
+    if (!rng || n < 1) return mclust_restricted_core(y_in, n, cfg, out, cls);
+    int constant = 1;
+    for (int i = 1; i < n; i++) if (y_in[i] != y_in[0]) { constant = 0; break; }
+    if (!constant) return mclust_restricted_core(y_in, n, cfg, out, cls);
+    double* yj = (double*)malloc(sizeof(double) * (size_t)n);
+    memcpy(yj, y_in, sizeof(double) * (size_t)n);
+    orc_jitter_if_constant(yj, n, rng);
+    if (jittered) *jittered = 1;
+    int rc = mclust_restricted_core(yj, n, cfg, out, cls);
+    free(yj);
+    return rc;
+}
+
+/* without an RNG the jitter cannot be drawn: a constant vector then has no valid model (returns -1), which the batch
+   drivers report; scDD() itself never gets here on observed data (skipConstant, R/scDD.R:292-310). */
 int orc_mclust_restricted(const double* y_in, int32_t n, const orc_cfg* cfg, orc_fit* out, int32_t* cls) {
-    /* :48-50 jitter when all values identical consumes the caller's RNG; the batch drivers
-       never reach here with constant vectors (skipConstant, R/scDD.R:292-310) except inside
-       permutations, where it is counted and reported by the caller. Not applied here. */
+    return mclust_restricted_core(y_in, n, cfg, out, cls);
+}
+
+static int mclust_restricted_core(const double* y_in, int32_t n, const orc_cfg* cfg, orc_fit* out, int32_t* cls) {
     const double* y = y_in;
     orc_row rows[ORC_GMAX];
     int32_t* labels = (int32_t*)malloc(sizeof(int32_t) * (size_t)n * ORC_GMAX);
@@ -828,73 +867,42 @@ int orc_genefit_batch(const double* logy, const int32_t* cond, const int64_t* ge
     return rc;
 }
 
-/* permMclustGene, unadjusted branch, R/permutations.R:273-282 */
-int orc_perm_batch(const double* logy, const int32_t* cond, const int64_t* gene_off, int32_t ngenes,
-                   int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
-                   const orc_cfg* cfg, double* bf_perm, int32_t nthreads) {
+/* permMclustGene (R/permutations.R:211-286), permMclust (:147-181), permMclustCov (:44-104).
+   seed_mode 0: seed6 is [ngenes*6], gene g draws all its B permutations from its own stream (parallelBy = "Genes":
+                bplapply over genes, R/scDD.R:458).
+   seed_mode 1: seed6 is [B*6], permutation b of EVERY gene is drawn from the start of stream b (parallelBy =
+                "Permutations": scDD loops over the genes in the master and each permMclust / permMclustCov call runs
+                bplapply(1:nperms, ...) under the same RNGseed, R/permutations.R:99,177).
+   In both modes a permuted subset with identical values draws its runif jitter from the stream it runs under
+   (orc_mclust_restricted_rng); with host-drawn permutations (perm_idx) no stream exists and such a set fails.
+   n_jittered (nullable) counts the jittered fit-sets. */
+static int perm_batch_any(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
+                          int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
+                          int32_t seed_mode, const orc_cfg* cfg, double* bf_perm, int32_t nthreads,
+                          int64_t* n_jittered, double* jp_terms) {
     int nt = set_threads(nthreads);
     int rc = 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    long long njit = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : njit)
     for (int g = 0; g < ngenes; g++) {
         int64_t o = gene_off[g];
         int n = (int)(gene_off[g + 1] - o);
         const double* y = logy + o;
         const int32_t* c = cond + o;
-        double* y1 = (double*)malloc(sizeof(double) * (n + 1));
-        double* y2 = (double*)malloc(sizeof(double) * (n + 1));
-        int32_t* k1 = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
-        int32_t* k2 = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
-        int32_t* nw = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
-        orc_rng rng;
-        if (seed6) orc_rng_set_lecuyer(&rng, seed6 + 6 * (size_t)g);
-        orc_fit f1, f2;
-        for (int b = 0; b < B; b++) {
-            const int32_t* pi;
-            if (perm_idx) pi = perm_idx + ((size_t)o * B + (size_t)b * n);
-            else { orc_sample_perm(&rng, n, nw); pi = nw; }             /* :273 new <- sample(1:length(y)) */
-            int n1 = 0, n2 = 0;
-            for (int i = 0; i < n; i++) {                                /* :274-276 */
-                double v = y[pi[i] - 1];
-                if (c[i] == 0) y1[n1++] = v; else y2[n2++] = v;
-            }
-            int r1 = orc_mclust_restricted(y1, n1, cfg, &f1, k1);        /* :278 */
-            int r2 = orc_mclust_restricted(y2, n2, cfg, &f2, k2);        /* :279 */
-            if (r1 || r2) {
-#pragma omp atomic write
-                rc = -1;
-            }
-            bf_perm[(size_t)g * B + b] =
-                orc_joint_posterior(y1, k1, n1, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0) +
-                orc_joint_posterior(y2, k2, n2, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0);   /* :281-282 */
+        double* fit = NULL; double* res = NULL;
+        if (cdr) {
+            /* lm(y ~ C): least squares with intercept (R uses Householder QR; same estimate up to rounding) */
+            const double* C = cdr + o;
+            long double sx = 0, sy = 0;
+            for (int i = 0; i < n; i++) { sx += C[i]; sy += y[i]; }
+            double mx = (double)(sx / n), my = (double)(sy / n);
+            long double sxx = 0, sxy = 0;
+            for (int i = 0; i < n; i++) { sxx += (C[i] - mx) * (C[i] - mx); sxy += (C[i] - mx) * (y[i] - my); }
+            double b1 = (double)(sxy / sxx), b0 = my - b1 * mx;
+            fit = (double*)malloc(sizeof(double) * (n + 1));
+            res = (double*)malloc(sizeof(double) * (n + 1));
+            for (int i = 0; i < n; i++) { fit[i] = b0 + b1 * C[i]; res[i] = y[i] - fit[i]; }
         }
-        free(y1); free(y2); free(k1); free(k2); free(nw);
-    }
-    return rc;
-}
-
-/* permMclustGene adjusted branch R/permutations.R:230-267 (== permMclustCov :44-104) */
-int orc_perm_batch_cov(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
-                       int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
-                       const orc_cfg* cfg, double* bf_perm, int32_t nthreads) {
-    int nt = set_threads(nthreads);
-    int rc = 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
-    for (int g = 0; g < ngenes; g++) {
-        int64_t o = gene_off[g];
-        int n = (int)(gene_off[g + 1] - o);
-        const double* y = logy + o;
-        const int32_t* c = cond + o;
-        const double* C = cdr + o;
-        /* lm(y ~ C): least squares with intercept (R uses Householder QR; same estimate up to rounding) */
-        long double sx = 0, sy = 0;
-        for (int i = 0; i < n; i++) { sx += C[i]; sy += y[i]; }
-        double mx = (double)(sx / n), my = (double)(sy / n);
-        long double sxx = 0, sxy = 0;
-        for (int i = 0; i < n; i++) { sxx += (C[i] - mx) * (C[i] - mx); sxy += (C[i] - mx) * (y[i] - my); }
-        double b1 = (double)(sxy / sxx), b0 = my - b1 * mx;
-        double* fit = (double*)malloc(sizeof(double) * (n + 1));
-        double* res = (double*)malloc(sizeof(double) * (n + 1));
-        for (int i = 0; i < n; i++) { fit[i] = b0 + b1 * C[i]; res[i] = y[i] - fit[i]; }
         double* ya = (double*)malloc(sizeof(double) * (n + 1));
         double* y1 = (double*)malloc(sizeof(double) * (n + 1));
         double* y2 = (double*)malloc(sizeof(double) * (n + 1));
@@ -903,34 +911,71 @@ int orc_perm_batch_cov(const double* logy, const int32_t* cond, const double* cd
         int32_t* k2 = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
         int32_t* nw = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
         orc_rng rng;
-        if (seed6) orc_rng_set_lecuyer(&rng, seed6 + 6 * (size_t)g);
+        if (seed6 && seed_mode == 0) orc_rng_set_lecuyer(&rng, seed6 + 6 * (size_t)g);
         orc_fit f0, f1, f2;
         for (int b = 0; b < B; b++) {
             const int32_t* pi;
+            if (seed6 && seed_mode == 1) orc_rng_set_lecuyer(&rng, seed6 + 6 * (size_t)b);
             if (perm_idx) pi = perm_idx + ((size_t)o * B + (size_t)b * n);
-            else { orc_sample_perm(&rng, n, nw); pi = nw; }             /* :243 sample(residuals(model)) */
+            else { orc_sample_perm(&rng, n, nw); pi = nw; }             /* :273 sample(1:length(y)) / :243 sample(residuals) */
             int n1 = 0, n2 = 0;
-            for (int i = 0; i < n; i++) {
-                double v = log(exp(fit[i] + res[pi[i] - 1]));            /* :244, :252-253 exp -> log round trip */
+            for (int i = 0; i < n; i++) {                                /* :274-276 / :244-253 */
+                double v = cdr ? log(exp(fit[i] + res[pi[i] - 1])) : y[pi[i] - 1];
                 if (c[i] == 0) y1[n1++] = v; else y2[n2++] = v;
             }
-            memcpy(ya, y1, sizeof(double) * n1);                         /* c(y1, y2) :261 */
-            memcpy(ya + n1, y2, sizeof(double) * n2);
-            int r0 = orc_mclust_restricted(ya, n, cfg, &f0, k0);
-            int r1 = orc_mclust_restricted(y1, n1, cfg, &f1, k1);
-            int r2 = orc_mclust_restricted(y2, n2, cfg, &f2, k2);
+            orc_rng* rp = perm_idx ? NULL : &rng;
+            int32_t j0 = 0, j1 = 0, j2 = 0;
+            int r0 = 0;
+            double jp0 = 0.0;
+            if (cdr) {
+                memcpy(ya, y1, sizeof(double) * n1);                     /* c(y1, y2) :261 */
+                memcpy(ya + n1, y2, sizeof(double) * n2);
+                r0 = orc_mclust_restricted_rng(ya, n, cfg, &f0, k0, rp, &j0);                 /* :261 (oa first) */
+            }
+            int r1 = orc_mclust_restricted_rng(y1, n1, cfg, &f1, k1, rp, &j1);                /* :278 / :262 */
+            int r2 = orc_mclust_restricted_rng(y2, n2, cfg, &f2, k2, rp, &j2);                /* :279 / :263 */
+            njit += j0 + j1 + j2;
             if (r0 || r1 || r2) {
 #pragma omp atomic write
                 rc = -1;
             }
-            bf_perm[(size_t)g * B + b] =
-                orc_joint_posterior(y1, k1, n1, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0) +
-                orc_joint_posterior(y2, k2, n2, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0) -
-                orc_joint_posterior(ya, k0, n, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0);    /* :265-267 */
+            if (cdr) jp0 = orc_joint_posterior(ya, k0, n, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0);
+            double jp1 = orc_joint_posterior(y1, k1, n1, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0);
+            double jp2 = orc_joint_posterior(y2, k2, n2, cfg->alpha, cfg->m0, cfg->s0, cfg->a0, cfg->b0);
+            double v = jp1 + jp2;                                                                 /* :281-282 */
+            if (cdr) v = v - jp0;                                                                 /* :265-267 */
+            if (r0 || r1 || r2) v = NAN;
+            if (jp_terms) {
+                const int sets = cdr ? 3 : 2;
+                double* t = jp_terms + ((size_t)g * B + b) * sets;
+                t[0] = r1 ? NAN : jp1; t[1] = r2 ? NAN : jp2;
+                if (cdr) t[2] = r0 ? NAN : jp0;
+            }
+            bf_perm[(size_t)g * B + b] = v;
         }
         free(fit); free(res); free(ya); free(y1); free(y2); free(k0); free(k1); free(k2); free(nw);
     }
+    if (n_jittered) *n_jittered = njit;
     return rc;
+}
+
+int orc_perm_batch(const double* logy, const int32_t* cond, const int64_t* gene_off, int32_t ngenes,
+                   int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
+                   const orc_cfg* cfg, double* bf_perm, int32_t nthreads) {
+    return perm_batch_any(logy, cond, NULL, gene_off, ngenes, B, perm_idx, seed6, 0, cfg, bf_perm, nthreads, NULL, NULL);
+}
+
+int orc_perm_batch_cov(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
+                       int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
+                       const orc_cfg* cfg, double* bf_perm, int32_t nthreads) {
+    return perm_batch_any(logy, cond, cdr, gene_off, ngenes, B, perm_idx, seed6, 0, cfg, bf_perm, nthreads, NULL, NULL);
+}
+
+int orc_perm_batch_ex(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
+                      int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6, int32_t seed_mode,
+                      const orc_cfg* cfg, double* bf_perm, int32_t nthreads, int64_t* n_jittered, double* jp_terms) {
+    return perm_batch_any(logy, cond, cdr, gene_off, ngenes, B, perm_idx, seed6, seed_mode, cfg, bf_perm, nthreads,
+                          n_jittered, jp_terms);
 }
 
 /* testKS onegene, R/Test_KS.R:56-65 (inclZero = FALSE form: callers pass nonzero raw values) */

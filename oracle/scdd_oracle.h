@@ -98,6 +98,13 @@ void orc_sample_perm(orc_rng* r, int32_t n, int32_t* out);        /* sample(1:n)
 void orc_lecuyer_next_stream(const uint32_t* in6, uint32_t* out6);    /* parallel::nextRNGStream */
 void orc_lecuyer_next_substream(const uint32_t* in6, uint32_t* out6); /* parallel::nextRNGSubStream */
 
+/* mclustRestricted under a live RNG stream: applies the `runif(n, -0.1, 0.1)` jitter of R/mclust.restricted.R:48-50
+ * to a local copy when all values are identical (rng == NULL: no jitter, such a vector has no valid model).
+ * *jittered (nullable) reports whether the jitter fired. */
+int orc_mclust_restricted_rng(const double* y, int32_t n, const orc_cfg* cfg, orc_fit* out, int32_t* cls,
+                              orc_rng* rng, int32_t* jittered);
+int orc_jitter_if_constant(double* y, int32_t n, orc_rng* rng);
+
 /* ---- batch drivers (OpenMP over genes; double as the CPU baseline) ---- */
 /* genes in CSR form: logy/cond hold, per gene, the log nonzero values in cell order and
  * cond (0 = reference condition, 1 = other) of those cells. */
@@ -118,6 +125,17 @@ int orc_perm_batch(const double* logy, const int32_t* cond, const int64_t* gene_
 int orc_perm_batch_cov(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
                        int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6,
                        const orc_cfg* cfg, double* bf_perm, int32_t nthreads);
+
+/* Both permutation drivers with the options the plain entry points fix:
+ *   cdr        NULL = unadjusted (permMclustGene / permMclust), else the adjusted branch (permMclustCov)
+ *   seed_mode  0: seed6 = [ngenes*6], one stream per gene (parallelBy = "Genes", R/scDD.R:458)
+ *              1: seed6 = [B*6], permutation b of every gene starts stream b (parallelBy = "Permutations",
+ *                 bplapply(1:nperms) inside permMclust / permMclustCov, R/permutations.R:177, :99)
+ *   n_jittered (nullable) number of fit-sets that drew the constant-vector jitter from their stream
+ *   jp_terms   (nullable) [ngenes*B*sets] the jointPosterior terms of every gene-permutation: JP(c1), JP(c2)[, JP(oa)] */
+int orc_perm_batch_ex(const double* logy, const int32_t* cond, const double* cdr, const int64_t* gene_off,
+                      int32_t ngenes, int32_t B, const int32_t* perm_idx, const uint32_t* seed6, int32_t seed_mode,
+                      const orc_cfg* cfg, double* bf_perm, int32_t nthreads, int64_t* n_jittered, double* jp_terms);
 
 /* R/Test_KS.R:56-65 on raw nonzero values */
 int orc_ks_batch(const double* vals, const int32_t* cond, const int64_t* gene_off, int32_t ngenes,

@@ -15,8 +15,9 @@ GMAX = 5
 _LIB = None
 
 ERRORS = {-1: "SCDD_ERR_NO_DEVICE", -2: "SCDD_ERR_BAD_ARG", -3: "SCDD_ERR_CUDA", -4: "SCDD_ERR_TOO_LARGE",
-          -5: "SCDD_ERR_FIT_FAILED"}
+          -5: "SCDD_ERR_FIT_FAILED", -6: "SCDD_ERR_INTERRUPTED"}
 ERR_FIT_FAILED = -5
+ERR_INTERRUPTED = -6
 
 
 class ScddError(RuntimeError):
@@ -37,6 +38,14 @@ class Fit(C.Structure):
                 ("mean", C.c_double * GMAX), ("var", C.c_double * GMAX)]
 
 
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
+
+
+class PermOpts(C.Structure):
+    _fields_ = [("seed_mode", C.c_int32), ("reserved", C.c_int32), ("jp_terms", C.c_void_p),
+                ("interrupt", INTERRUPT_FN), ("interrupt_arg", C.c_void_p)]
+
+
 STATS_FIELDS = ["triples", "point_iters", "fit_sets", "em_iters", "iter_cap_hits", "tol_near", "bic_near",
                 "const_sets", "failed_sets", "fit_kernel_ms", "fit_kernel_launches", "rng_kernel_ms", "total_ms",
                 "h2d_bytes", "d2h_bytes", "debug_violations"]
@@ -54,7 +63,7 @@ FIT_DTYPE = np.dtype([("G", np.int32), ("model_v", np.int32), ("n", np.int32), (
                       ("var", np.float64, (GMAX,))])
 
 EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set_devices", "scdd_default_cfg",
-           "scdd_fit_observed", "scdd_perm_bf", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
+           "scdd_fit_observed", "scdd_perm_bf", "scdd_perm_bf_ex", "scdd_release_cache", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
            "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax",
            "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
@@ -81,6 +90,9 @@ def lib():
     L.scdd_default_cfg.restype = None
     L.scdd_fit_observed.argtypes = [vp, vp, vp, C.c_int32, C.POINTER(Cfg), vp, vp, vp, vp, vp, C.POINTER(Stats)]
     L.scdd_perm_bf.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Cfg), vp, vp, C.POINTER(Stats)]
+    L.scdd_perm_bf_ex.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Cfg), C.POINTER(PermOpts), vp, vp,
+                                  C.POINTER(Stats)]
+    L.scdd_release_cache.restype = None
     L.scdd_ks.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(Stats)]
     L.scdd_rng_gene_seeds.argtypes = [C.c_uint32, C.c_int32, vp]
     L.scdd_rng_sample_perms.argtypes = [vp, C.c_int32, C.c_int32, vp]

@@ -206,16 +206,32 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         msg("Performing permutations to evaluate independence of clustering and condition for each gene")
         msg(f"Parallelizing by {parallelBy}")
         seed = int(param.get("RNGseed", 1))
-        seeds = hp.gene_seeds(seed, nf)
+        # RNG-stream shape of the two dispatch modes: "Genes" = one L'Ecuyer-CMRG stream per gene
+        # (bplapply over genes, R/scDD.R:458); "Permutations" = permutation b of EVERY gene from stream b, because
+        # scDD() loops over the genes and each permMclust / permMclustCov call runs bplapply(1:nperms) under the same
+        # RNGseed (R/scDD.R:414-455, R/permutations.R:177, :99)
+        by_perm = parallelBy == "Permutations"
+        seeds = hp.gene_seeds(seed, permutations if by_perm else nf)
         if perm_source == "host":
-            perm_idx = np.concatenate([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), permutations)[0].ravel()
-                                       for g in range(nf)]) if nf else np.zeros(0, dtype=np.int32)
-            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, perm_idx=perm_idx, cdr=cdr, cfg=cfg)
+            def draw(g):
+                n = int(off[g + 1] - off[g])
+                if by_perm:
+                    return np.stack([hp.sample_perms(seeds[b], n, 1)[0][0] for b in range(permutations)]).ravel()
+                return hp.sample_perms(seeds[g], n, permutations)[0].ravel()
+            perm_idx = np.concatenate([draw(g) for g in range(nf)]) if nf else np.zeros(0, dtype=np.int32)
+            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, perm_idx=perm_idx, cdr=cdr, cfg=cfg, allow_failed=True)
         else:
-            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, seed6=seeds, cdr=cdr, cfg=cfg)
+            bf_perm, st = hp.perm_bf(logy, c01, off, permutations, seed6=seeds, cdr=cdr, cfg=cfg, allow_failed=True,
+                                     seed_mode=int(by_perm), interrupt=param.get("interrupt"))
+        if st["const_sets"] > 0:
+            msg(f"Notice: {int(st['const_sets'])} permuted subsets had identical values and were jittered "
+                f"(runif(-0.1, 0.1), as mclustRestricted does)")
+        if st["failed_sets"] > 0:
+            msg(f"Warning: {int(st['failed_sets'])} permuted fit-sets had no valid model; the p-values of their genes are NA")
         stats["permutations"] = st
         obs = (bf - den) if adjust_perms else bf                      # R/scDD.R:467-473
         pvals = (bf_perm > obs[:, None]).sum(axis=1) / float(permutations)
+        pvals = np.where(np.isnan(bf_perm).any(axis=1) | np.isnan(obs), np.nan, pvals)   # R: sum() over an NA is NA
         sig = np.nonzero(p_adjust_BH(pvals) < level)[0]
     pvals_all = np.full(ngenes, np.nan)
     pvals_all[tofit] = pvals

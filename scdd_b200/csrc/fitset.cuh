@@ -900,7 +900,10 @@ __device__ __forceinline__ void mean_order(const Row& mc, int comps, int* ord) {
 // R/joint.posterior.R:35-64 on the relabelled classes of the selected model.
 // Quirk kept: the loop runs over labels 1..r with r = number of DISTINCT labels, so a gap in the label
 // set gives nk = 0 -> lgamma(0) = Inf (and cells of labels > r are not counted).
-__device__ __noinline__ double joint_posterior(const Row& mc, int comps, const DevCfg& cfg) {
+// jittered: the fit ran on y + runif jitter (all y identical = yconst, R/mclust.restricted.R:48-50) but the score is
+// taken on the original values: sum(y[class == k]) = nk * yconst, sum(y[class == k]^2) = nk * yconst^2.
+__device__ __noinline__ double joint_posterior(const Row& mc, int comps, const DevCfg& cfg, bool jittered = false,
+                                               double yconst = 0.0) {
     int ord[GMAX];
     mean_order(mc, comps, ord);
     double nk[GMAX], sy[GMAX], syy[GMAX];
@@ -912,6 +915,7 @@ __device__ __noinline__ double joint_posterior(const Row& mc, int comps, const D
         // cl2[cl == l] <- as.numeric(names(mean[order(mean)])[l])  (order(), not rank(): quirk viii)
         int nl = (comps > 1) ? ord[l] : l;
         nk[nl] = mc.cnt[l]; sy[nl] = mc.sy[l]; syy[nl] = mc.syy[l];
+        if (jittered) { sy[nl] = __dmul_rn(mc.cnt[l], yconst); syy[nl] = __dmul_rn(mc.cnt[l], __dmul_rn(yconst, yconst)); }
         if (mc.cnt[l] > 0.0) r++;
     }
     const double alpha = cfg.alpha, m0 = cfg.m0, s0 = cfg.s0, a0 = cfg.a0, b0 = cfg.b0;

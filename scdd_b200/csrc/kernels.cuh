@@ -104,94 +104,185 @@ __global__ void permgen_kernel(const int64_t* __restrict__ off, int ngenes, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// permutations, warp per gene.  R's stream is serial per gene, but only the Fisher-Yates consumption has
-// to be: the MRG32k3a outputs themselves are produced 32 at a time.  Decimating a linear recurrence of
-// order 3 by 32 gives another order-3 recurrence, z[j+3] = b2 z[j+2] + b1 z[j+1] + b0 z[j] (mod m), whose
-// coefficients are those of the characteristic polynomial of A^32 (computed on the host); lane l produces
-// outputs l, l+32, l+64, ... of the stream.  Lane 0 then consumes the 16-bit chunks exactly as
-// R_unif_index / do_sample do, with the Fisher-Yates array in shared memory, and the finished permutation
-// is written out coalesced by the whole warp.  Bit-identical to permgen_kernel and to R.
+// permutations, a group of GS lanes per gene (GS = 32, 8 or 4; 32 / GS genes per warp).
+//
+// R's stream is serial per gene, but only the Fisher-Yates consumption has to be: the MRG32k3a outputs themselves
+// are produced GS at a time.  Decimating a linear recurrence of order 3 by GS gives another order-3 recurrence,
+// z[j+3] = b2 z[j+2] + b1 z[j+1] + b0 z[j] (mod m), whose coefficients are those of the characteristic polynomial of
+// A^GS (computed on the host); lane l of the group produces outputs l, l+GS, l+2GS, ... of the stream.  The group's
+// leader lane then consumes the 16-bit chunks exactly as R_unif_index / do_sample do, with the Fisher-Yates array in
+// shared memory, and the finished permutation is written out by the whole group.  With GS < 32 the leaders of the
+// 32 / GS groups of a warp run the serial loop in lock-step, each on its own gene: the issue slots the loop costs
+// (it is issue-bound: ~25 instructions per candidate) are shared by 4 or 8 genes instead of one.
+// Bit-identical to permgen_kernel and to R.
+//
+// seed_mode 0: seeds = [ngenes*6], gene g continues its own stream over the permutations of all chunks (the advanced
+//              state is written back) -- BiocParallel's stream per bplapply element, parallelBy = "Genes".
+// seed_mode 1: seeds = [B*6], permutation b of every gene starts stream b afresh -- bplapply(1:nperms) inside
+//              permMclust / permMclustCov, parallelBy = "Permutations" (R/permutations.R:177, :99).
+//
+// Constant subsets (R/mclust.restricted.R:48-50): when all values of a permuted subset are identical the reference
+// adds runif(n, -0.1, 0.1), drawn from the SAME stream between this permutation's sample() and the next one's.  The
+// leader therefore tests each subset of the permutation it just drew (first two values, then the rest: one compare
+// per permutation on untied data), and for a constant subset records the stream state at that point in
+// jit_state[item] -- fit_kernel regenerates the n uniforms from it -- and skips n outputs of its own stream.
 // ------------------------------------------------------------------------------------------------
 struct MrgDecim {
     uint32_t b1[3], b2[3];   // {b0, b1, b2} for the two components (moduli MRG_M1, MRG_M2)
 };
 
-constexpr int PG_BLOCK = 256;   // uniforms generated per refill (8 per lane)
+constexpr int PG_BLOCK = 256;   // uniforms generated per refill and gene
+constexpr uint32_t JIT_NONE = 0xffffffffu;   // jit_state[6 * item]: no jitter recorded (not a valid MRG component)
 
-__device__ __forceinline__ uint32_t mrg_rec3(const uint32_t* c, uint32_t z0, uint32_t z1, uint32_t z2, uint64_t m) {
-    uint64_t s = ((uint64_t)c[0] * z0) % m + ((uint64_t)c[1] * z1) % m + ((uint64_t)c[2] * z2) % m;
-    return (uint32_t)(s % m);
+// x mod (2^32 - c) for the two MRG moduli (c = 209, 22853): 2^32 = c (mod m), so hi * 2^32 + lo = hi * c + lo
+__device__ __forceinline__ uint64_t mrg_fold(uint64_t x, uint32_t c) { return (x >> 32) * c + (x & 0xffffffffULL); }
+__device__ __forceinline__ uint32_t mrg_rec3(const uint32_t* co, uint32_t z0, uint32_t z1, uint32_t z2, uint32_t c) {
+    // each folded product < 2^32 (c + 1); their sum < 2^49; second fold < 2^33; third < 2^32 + c
+    uint64_t s = mrg_fold((uint64_t)co[0] * z0, c) + mrg_fold((uint64_t)co[1] * z1, c) + mrg_fold((uint64_t)co[2] * z2, c);
+    s = mrg_fold(mrg_fold(s, c), c);
+    const uint64_t m = 4294967296ULL - c;
+    if (s >= m) s -= m;
+    return (uint32_t)s;
+}
+constexpr uint32_t MRG_C1 = (uint32_t)(4294967296LL - MRG_M1), MRG_C2 = (uint32_t)(4294967296LL - MRG_M2);
+
+__host__ __device__ constexpr size_t permgen_smem_per_group(int nmax, int idx_bytes, int gs) {
+    return ((size_t)nmax * idx_bytes + 15) / 16 * 16 + PG_BLOCK * sizeof(uint16_t) + (size_t)6 * gs * sizeof(uint32_t);
 }
 
-__host__ __device__ constexpr size_t permgen_smem_per_warp(int nmax, int idx_bytes) {
-    return ((size_t)nmax * idx_bytes + 15) / 16 * 16 + 2 * (PG_BLOCK + 3) * sizeof(uint32_t) + 8 +
-           PG_BLOCK * sizeof(uint16_t);
+struct PermgenArgs {
+    const int64_t* off;
+    int ngenes;
+    uint32_t* seeds;
+    int seed_mode;            // 0: per gene (in/out), 1: per permutation (read-only, indexed perm_b0 + b)
+    int perm_b0;
+    void* perm_out;           // gene g, local permutation b, element i -> [off_g * nb + b * n_g + i], 0-based
+    int nb;
+    MrgDecim dc;              // decimation by the group size
+    int nmax;
+    // constant-subset jitter; jit_state == nullptr switches the test off
+    const double* vals;
+    const double* fitted;     // adjusted path: the permuted quantity is log(exp(fitted[i] + vals[perm[i]]))
+    const uint32_t* part;
+    const int32_t* n1;
+    int sets;
+    uint32_t* jit_state;      // [ngenes * nb * sets * 6], pre-set to JIT_NONE
+};
+
+// the value the fit kernel will see at position j (partition order) of a subset -- same expression as fit_kernel's gather
+__device__ __forceinline__ double permuted_value(const double* vals, const double* fitted, int64_t o, uint32_t i, uint32_t src) {
+    double v = vals[o + src];
+    if (fitted) v = log(exp(fitted[o + i] + v));   // R/permutations.R:244,251-252
+    return v;
 }
 
-template <class IdxT>
-__global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes, uint32_t* __restrict__ seeds,
-                                    IdxT* __restrict__ perm_out, int nb, MrgDecim dc, int nmax) {
+template <class IdxT, int GS>
+__global__ void permgen_group_kernel(PermgenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GPW = 32 / GS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    unsigned char* base = smem_raw + warp * permgen_smem_per_warp(nmax, (int)sizeof(IdxT));
+    const int sub = lane / GS, sl = lane % GS, lead = lane - sl;
+    const bool leader = sl == 0;
+    unsigned char* base = smem_raw + (size_t)(warp * GPW + sub) * permgen_smem_per_group(a.nmax, (int)sizeof(IdxT), GS);
     IdxT* arr = reinterpret_cast<IdxT*>(base);
-    uint32_t* Xr = reinterpret_cast<uint32_t*>(base + ((size_t)nmax * sizeof(IdxT) + 15) / 16 * 16);
-    uint32_t* Yr = Xr + (PG_BLOCK + 3) + 1;
-    uint16_t* cand = reinterpret_cast<uint16_t*>(Yr + (PG_BLOCK + 3) + 1);
+    uint16_t* cand = reinterpret_cast<uint16_t*>(base + ((size_t)a.nmax * sizeof(IdxT) + 15) / 16 * 16);
+    uint32_t* ini = reinterpret_cast<uint32_t*>(cand + PG_BLOCK);   // [2][3 * GS] raw outputs of the first 3 GS steps
+    const int groups_total = gridDim.x * wpb * GPW;
 
-    for (int g = blockIdx.x * wpb + warp; g < ngenes; g += gridDim.x * wpb) {
-        const int64_t o = off[g];
-        const uint32_t n = (uint32_t)(off[g + 1] - o);
-        // ---- stream start: raw values X_0..X_98 / Y_0..Y_98 by plain stepping, then the lane windows ----
-        __syncwarp();
-        if (lane == 0) {
-            Lecuyer st;
-            for (int j = 0; j < 6; j++) st.s[j] = seeds[(size_t)g * 6 + j];
-            Xr[0] = st.s[0]; Xr[1] = st.s[1]; Xr[2] = st.s[2];
-            Yr[0] = st.s[3]; Yr[1] = st.s[4]; Yr[2] = st.s[5];
-            for (int t = 0; t < 96; t++) {
-                lecuyer_unif(st);
-                Xr[3 + t] = st.s[2];
-                Yr[3 + t] = st.s[5];
+    for (int gb = (blockIdx.x * wpb + warp) * GPW; gb < a.ngenes; gb += groups_total) {   // warp-uniform
+        const int g = gb + sub;
+        const bool act = g < a.ngenes;
+        int64_t o = 0;
+        uint32_t n = 0;
+        if (act) { o = a.off[g]; n = (uint32_t)(a.off[g + 1] - o); }
+        int nh0 = 0;
+        if (act && a.jit_state) nh0 = a.n1[g];
+        uint32_t x0 = 0, x1 = 0, x2 = 0, y0 = 0, y1 = 0, y2 = 0;   // this lane's window of the decimated sequences
+        uint32_t xl = 0, yl = 0;                                  // raw values of the lane's last generated output
+        uint32_t bs[6] = {0, 0, 0, 0, 0, 0};    // stream state at the start of the block held in cand (leader)
+        uint32_t nbs[6] = {0, 0, 0, 0, 0, 0};   // ... of the block after it
+        int used = PG_BLOCK;
+        bool have_block = false;
+
+        // stream start: the leader steps 3 GS outputs serially, the lanes pick up their windows
+        auto init_stream = [&](const uint32_t* seed) {
+            __syncwarp();
+            if (leader && act) {
+                Lecuyer st;
+#pragma unroll
+                for (int j = 0; j < 6; j++) { st.s[j] = seed[j]; bs[j] = seed[j]; }
+                for (int t = 0; t < 3 * GS; t++) {
+                    lecuyer_unif(st);
+                    ini[t] = st.s[2];
+                    ini[3 * GS + t] = st.s[5];
+                }
             }
-        }
-        __syncwarp();
-        uint32_t x0 = Xr[3 + lane], x1 = Xr[35 + lane], x2 = Xr[67 + lane];
-        uint32_t y0 = Yr[3 + lane], y1 = Yr[35 + lane], y2 = Yr[67 + lane];
-        __syncwarp();
-        int used = PG_BLOCK;          // forces a refill first
-        bool first_block = true;
-        IdxT* gout = perm_out + (size_t)o * nb;
-        for (int b = 0; b < nb; b++) {
-            for (uint32_t i = lane; i < n; i += 32) arr[i] = (IdxT)i;
+            __syncwarp();
+            if (act) {
+                x0 = ini[sl]; x1 = ini[GS + sl]; x2 = ini[2 * GS + sl];
+                y0 = ini[3 * GS + sl]; y1 = ini[4 * GS + sl]; y2 = ini[5 * GS + sl];
+            }
+            used = PG_BLOCK;
+            have_block = false;
+            __syncwarp();
+        };
+        // next PG_BLOCK outputs of the groups that ask for them (want is group-uniform; called warp-uniformly)
+        auto refill = [&](bool want) {
+            if (!__any_sync(FULLMASK, want)) return;
+            if (want) {
+#pragma unroll 1
+                for (int j = 0; j < PG_BLOCK / GS; j++) {
+                    const int t = GS * j + sl;
+                    const int64_t p1 = (int64_t)x0, p2 = (int64_t)y0;
+                    const int64_t d = (p1 > p2) ? (p1 - p2) : (p1 - p2 + MRG_M1);
+                    const double u = r_fixup((double)d * 2.328306549295727688e-10);
+                    cand[t] = (uint16_t)(int)floor(u * 65536.0);
+                    xl = x0; yl = y0;
+                    const uint32_t xn = mrg_rec3(a.dc.b1, x0, x1, x2, MRG_C1);
+                    const uint32_t yn = mrg_rec3(a.dc.b2, y0, y1, y2, MRG_C2);
+                    x0 = x1; x1 = x2; x2 = xn;
+                    y0 = y1; y1 = y2; y2 = yn;
+                }
+            }
+            __syncwarp();
+            // the state after this block = its last three raw outputs (lanes GS-3 .. GS-1 of the last round)
+            uint32_t t6[6];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                t6[k] = __shfl_sync(FULLMASK, xl, lead + GS - 3 + k);
+                t6[3 + k] = __shfl_sync(FULLMASK, yl, lead + GS - 3 + k);
+            }
+            if (want) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { if (have_block) bs[k] = nbs[k]; nbs[k] = t6[k]; }
+                have_block = true;
+                used = 0;
+            }
+        };
+        // state after `used` outputs of the current block (leader; at most PG_BLOCK serial steps, rarely needed)
+        auto state_now = [&](uint32_t* out6) {
+            Lecuyer st;
+#pragma unroll
+            for (int j = 0; j < 6; j++) st.s[j] = (used == PG_BLOCK && have_block) ? nbs[j] : bs[j];
+            if (!(used == PG_BLOCK && have_block))
+                for (int t = 0; t < used && have_block; t++) lecuyer_unif(st);
+#pragma unroll
+            for (int j = 0; j < 6; j++) out6[j] = st.s[j];
+        };
+
+        if (a.seed_mode == 0) init_stream(a.seeds + (size_t)(act ? g : 0) * 6);
+        IdxT* gout = reinterpret_cast<IdxT*>(a.perm_out) + (size_t)o * a.nb;
+        for (int b = 0; b < a.nb; b++) {
+            if (a.seed_mode != 0) init_stream(a.seeds + (size_t)(a.perm_b0 + b) * 6);
+            for (uint32_t i = sl; i < n; i += GS) arr[i] = (IdxT)i;
             __syncwarp();
             uint32_t i = 0, m = n;
             int bits = index_bits(m);
             int need = bits / 16 + 1;
             uint64_t vacc = 0;
-            while (i < n) {
-                if (used == PG_BLOCK) {
-                    // ---- refill: 8 outputs per lane ----
-                    if (!first_block && lane < 3) { Xr[lane] = Xr[PG_BLOCK + lane]; Yr[lane] = Yr[PG_BLOCK + lane]; }
-                    first_block = false;
-                    __syncwarp();
-#pragma unroll 1
-                    for (int j = 0; j < PG_BLOCK / 32; j++) {
-                        const int t = 32 * j + lane;
-                        Xr[3 + t] = x0; Yr[3 + t] = y0;
-                        int64_t p1 = (int64_t)x0, p2 = (int64_t)y0;
-                        int64_t d = (p1 > p2) ? (p1 - p2) : (p1 - p2 + MRG_M1);
-                        double u = r_fixup((double)d * 2.328306549295727688e-10);
-                        cand[t] = (uint16_t)(int)floor(u * 65536.0);
-                        uint32_t xn = mrg_rec3(dc.b1, x0, x1, x2, (uint64_t)MRG_M1);
-                        uint32_t yn = mrg_rec3(dc.b2, y0, y1, y2, (uint64_t)MRG_M2);
-                        x0 = x1; x1 = x2; x2 = xn;
-                        y0 = y1; y1 = y2; y2 = yn;
-                    }
-                    used = 0;
-                    __syncwarp();
-                }
-                if (lane == 0) {
+            while (__any_sync(FULLMASK, act && i < n)) {
+                refill(act && i < n && used == PG_BLOCK);
+                if (leader && act && i < n) {
                     // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
                     if (n <= 32768u) {
                         // ceil(log2 m) <= 15: one 16-bit chunk per attempt, everything fits 32-bit arithmetic
@@ -236,21 +327,46 @@ __global__ void permgen_warp_kernel(const int64_t* __restrict__ off, int ngenes,
                         }
                     }
                 }
-                i = __shfl_sync(FULLMASK, i, 0);
-                used = __shfl_sync(FULLMASK, used, 0);
+                i = __shfl_sync(FULLMASK, i, lead);
+                used = __shfl_sync(FULLMASK, used, lead);
                 __syncwarp();
             }
-            for (uint32_t k = lane; k < n; k += 32) gout[(size_t)b * n + k] = arr[n - 1 - k];
+            for (uint32_t k = sl; k < n; k += GS) gout[(size_t)b * n + k] = arr[n - 1 - k];
             __syncwarp();
-        }
-        // ---- state after exactly the consumed outputs: (X_T, X_T+1, X_T+2), T = block start + used ----
-        if (lane == 0) {
-            // X_{Tb + used + k} for k = 0..2 live in Xr[used + k] (Xr[0..2] is the state at the block start)
-            for (int k = 0; k < 3; k++) {
-                seeds[(size_t)g * 6 + k] = Xr[used + k];
-                seeds[(size_t)g * 6 + 3 + k] = Yr[used + k];
+            if (a.jit_state) {
+                // subsets in the order the reference fits them: (oa,) c1, c2 -- R/permutations.R:261-263, :278-279
+                for (int q = 0; q < a.sets; q++) {
+                    const int w = (a.sets == 3) ? (q == 0 ? 2 : q - 1) : q;   // fit_kernel's set index: 0 = c1, 1 = c2, 2 = oa
+                    uint32_t skip = 0;
+                    if (leader && act) {
+                        const int nh = (w == 0) ? nh0 : (w == 1 ? (int)n - nh0 : (int)n);
+                        const int pofs = (w == 1) ? nh0 : 0;
+                        bool constant = nh >= 1;
+                        double v0 = 0.0;
+                        for (int j = 0; j < nh && constant; j++) {
+                            const uint32_t ci = a.part[o + pofs + j];
+                            const double v = permuted_value(a.vals, a.fitted, o, ci, (uint32_t)arr[n - 1 - ci]);
+                            if (j == 0) v0 = v; else if (v != v0) constant = false;
+                        }
+                        if (constant) {
+                            state_now(a.jit_state + (((size_t)g * a.nb + b) * a.sets + w) * 6);
+                            skip = (uint32_t)nh;
+                        }
+                    }
+                    skip = __shfl_sync(FULLMASK, skip, lead);
+                    while (__any_sync(FULLMASK, skip > 0)) {
+                        refill(skip > 0 && used == PG_BLOCK);
+                        if (skip > 0) {
+                            const uint32_t take = min(skip, (uint32_t)(PG_BLOCK - used));
+                            used += (int)take;
+                            skip -= take;
+                        }
+                    }
+                }
             }
         }
+        // ---- state after exactly the consumed outputs ----
+        if (a.seed_mode == 0 && leader && act) state_now(a.seeds + (size_t)g * 6);
         __syncwarp();
     }
 }
@@ -296,6 +412,10 @@ struct FitArgs {
     int iter_budget;           // 0 = none
     int only_deferred;
     unsigned char* deferred;   // [ngenes * nb * sets], nullable
+    // Constant subsets (R/mclust.restricted.R:48-50): stream state at which the reference draws runif(n, -0.1, 0.1),
+    // recorded by permgen_group_kernel per fit-set (JIT_NONE in word 0 = none); nullable (observed data, host-drawn
+    // permutations: a constant vector then has no valid model)
+    const uint32_t* jit_state;
 };
 
 __device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int n, int b, uint32_t i) {
@@ -396,8 +516,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
                 uint32_t i = a.part[o + pofs + j];
                 uint32_t src = perm_lookup(a, o, ng, b, i);
                 SCDD_CHECK(a.stats, i < (uint32_t)ng && src < (uint32_t)ng && np <= a.np_max);
-                v = a.vals[o + src];
-                if (a.fitted) v = log(exp(a.fitted[o + i] + v));   // R/permutations.R:244,251-252
+                v = permuted_value(a.vals, a.fitted, o, i, src);
             }
             xs[j] = v;
         }
@@ -406,11 +525,36 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
 
         double jp = NaN;
         int comps = 0;
+        // all values identical: the reference jitters with runif(n, -0.1, 0.1) drawn mid-stream
+        // (R/mclust.restricted.R:48-50).  With device-drawn permutations the stream state at that point was
+        // recorded by permgen_group_kernel and the n uniforms are regenerated here, in element order; the jittered
+        // copy is local to the fit (jointPosterior gets the identical values, R/permutations.R:278-282).
+        bool jittered = false;
+        double vconst = 0.0;
+        if (n >= 1 && xs[0] == xs[n - 1] && a.jit_state) {
+            const uint32_t* js = a.jit_state + (size_t)(((long long)g * a.nb + b) * a.sets + w) * 6;
+            if (js[0] != JIT_NONE) {       // team-uniform (global read of the same word)
+                jittered = true;
+                vconst = xs[0];
+                T::sync();
+                if (lead0) {
+                    Lecuyer rs;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) rs.s[j] = js[j];
+                    for (int j = 0; j < n; j++) {
+                        const double u = lecuyer_unif(rs);
+                        xs[j] = __dadd_rn(vconst, __dadd_rn(-0.1, __dmul_rn(0.2, u)));   // y + (a + (b - a) * unif_rand())
+                    }
+                }
+                T::sync();
+                team_sort<TW>(xs, np, lane);
+            }
+        }
         if (n < 1 || xs[0] == xs[n - 1]) {
-            // all values identical: the reference jitters with runif() (R/mclust.restricted.R:48-50),
-            // which consumes RNG state mid-stream; reported, never silently fitted
+            // no stream to draw the jitter from (observed data, host-drawn permutations): reported, never silently fitted
             if (lead0) { st->const_sets += 1.0; st->failed_sets += 1.0; st->fit_sets += 1.0; }
         } else {
+            if (jittered && lead0) st->const_sets += 1.0;
             if (BUDGET) {
                 WarpStats snap;
                 if (lead0) snap = *st;
@@ -423,7 +567,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             } else {
                 comps = fit_set<TW>(xs, n, lane, rows, a.cfg, st, pm, red);
             }
-            if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg);
+            if (comps > 0) jp = joint_posterior(rows[comps - 1], comps, a.cfg, jittered, vconst);
         }
         if (lead0) {
             a.jp[((long long)g * a.nb + b) * a.sets + w] = jp;
@@ -480,9 +624,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     }
 }
 
-// bf.perm[g, b] = JP(c1) + JP(c2) [- JP(oa)]   (R/permutations.R:265-267, :281-282)
+// bf.perm[g, b] = JP(c1) + JP(c2) [- JP(oa)]   (R/permutations.R:265-267, :281-282); jp_out (nullable) keeps the terms
 __global__ void combine_kernel(const double* __restrict__ jp, int ngenes, int nb, int sets,
-                               double* __restrict__ bf, long long ld, int col0) {
+                               double* __restrict__ bf, long long ld, int col0, double* __restrict__ jp_out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)ngenes * nb) return;
     int b = (int)(t % nb);
@@ -491,6 +635,10 @@ __global__ void combine_kernel(const double* __restrict__ jp, int ngenes, int nb
     double v = __dadd_rn(p[0], p[1]);
     if (sets == 3) v = __dsub_rn(v, p[2]);
     bf[g * ld + col0 + b] = v;
+    if (jp_out) {
+        double* q = jp_out + (g * ld + col0 + b) * sets;
+        for (int w = 0; w < sets; w++) q[w] = p[w];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

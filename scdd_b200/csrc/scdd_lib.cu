@@ -7,8 +7,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -29,6 +32,7 @@ using namespace scdd;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::vector<int> g_devices;   // empty = current device
+static std::mutex g_devices_mu;
 
 struct ScddError {
     int code;
@@ -141,9 +145,9 @@ void charpoly3(const Mat3& M, uint64_t m, uint32_t* b) {
     b[2] = (uint32_t)tr;
 }
 
-MrgDecim decimation_by_32() {
+MrgDecim decimation_by_pow2(int log2) {
     Mat3 A1, A2;
-    jump_matrices(5, A1, A2);   // A^(2^5) = A^32
+    jump_matrices(log2, A1, A2);   // A^(2^log2)
     MrgDecim d;
     charpoly3(A1, (uint64_t)MRG_M1, d.b1);
     charpoly3(A2, (uint64_t)MRG_M2, d.b2);
@@ -202,6 +206,10 @@ struct Pipeline {
     DevBuf<uint32_t> d_part, d_seeds;
     DevBuf<unsigned long long> d_counter;
     DevBuf<unsigned char> d_perm, d_scratch;
+    DevBuf<uint32_t> d_jit;          // stream states of the constant-subset jitter, per fit-set of a chunk
+    int seed_mode = 0;               // 0: one stream per gene, 1: one stream per permutation (parallelBy = "Permutations")
+    int perms_done = 0;              // permutations already processed (indexes the per-permutation seeds)
+    int n_seed_rows = 0;
     DevBuf<double> d_gene_cost;      // EM work per gene measured on the first chunk ...
     DevBuf<int32_t> d_gene_order;    // ... and the resulting longest-first gene order used by later chunks
     bool have_order = false;
@@ -392,39 +400,86 @@ struct Pipeline {
     }
 
     // device buffers for `bc` permutations per gene drawn on the device
-    void alloc_perm_chunk(int bc, const uint32_t* seed6, cudaStream_t s) {
+    // seed_rows: ngenes (mode 0) or the total number of permutations B (mode 1)
+    void alloc_perm_chunk(int bc, const uint32_t* seed6, cudaStream_t s, int mode = 0, int seed_rows = -1) {
         chunk_perms = bc;
+        seed_mode = mode;
+        perms_done = 0;
+        n_seed_rows = seed_rows < 0 ? ngenes : seed_rows;
         d_perm.alloc(nnz * (size_t)bc * idx_bytes());
         d_scratch.alloc(nnz * idx_bytes());
-        d_seeds.alloc((size_t)ngenes * 6);
-        CK(cudaMemcpyAsync(d_seeds.p, seed6, (size_t)ngenes * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        d_seeds.alloc((size_t)n_seed_rows * 6);
+        CK(cudaMemcpyAsync(d_seeds.p, seed6, (size_t)n_seed_rows * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         const int sets = adjusted ? 3 : 2;
         d_jp.alloc((size_t)ngenes * bc * sets);
+        d_jit.alloc((size_t)ngenes * bc * sets * 6);
     }
 
-    // permgen + fit + combine for nb permutations; bf_out[g * ld + col0 + b]
-    void run_chunk_device_perms(cudaStream_t s, int nb, double* bf_out, long long ld, int col0) {
+    // GS lanes per gene for permgen_group_kernel: the smallest group that still leaves several warps per SM
+    int pick_group_size() const {
+        const size_t cap = 200 * 1024;
+        const int ib = (int)idx_bytes();
+        auto fits = [&](int gs, size_t min_warps) {
+            return cap / (permgen_smem_per_group(max_n, ib, gs) * (32 / gs)) >= min_warps;
+        };
+        if (const char* e = std::getenv("SCDD_PERMGEN_GS")) {   // A/B switch; ignored when the genes do not fit
+            const int v = std::atoi(e);
+            if ((v == 4 || v == 8 || v == 32) && fits(v, 1)) return v;
+        }
+        for (int gs : {4, 8})
+            if (fits(gs, 4)) return gs;
+        return 32;
+    }
+
+    template <class IdxT, int GS>
+    void launch_permgen_gs(cudaStream_t s, PermgenArgs a) {
+        static const MrgDecim dc = decimation_by_pow2(GS == 32 ? 5 : (GS == 8 ? 3 : 2));
+        a.dc = dc;
+        const size_t cap = 200 * 1024;
+        const size_t per_warp = permgen_smem_per_group(max_n, (int)sizeof(IdxT), GS) * (32 / GS);
+        const int gpw = 32 / GS;
+        int wpb = (int)std::max<size_t>(1, std::min<size_t>(4, cap / per_warp));
+        wpb = std::max(1, std::min(wpb, (ngenes + gpw - 1) / gpw));
+        const size_t smem = per_warp * wpb;
+        const int blocks_needed = (ngenes + gpw * wpb - 1) / (gpw * wpb);
+        const int grid = std::min(blocks_needed, n_sm * std::max(1, std::min(16, (int)(cap / smem))));
+        CK(cudaFuncSetAttribute(permgen_group_kernel<IdxT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        permgen_group_kernel<IdxT, GS><<<grid, wpb * 32, smem, s>>>(a);
+    }
+    template <class IdxT>
+    void launch_permgen(cudaStream_t s, const PermgenArgs& a, int gs) {
+        if (gs == 4) launch_permgen_gs<IdxT, 4>(s, a);
+        else if (gs == 8) launch_permgen_gs<IdxT, 8>(s, a);
+        else launch_permgen_gs<IdxT, 32>(s, a);
+    }
+
+    // permgen + fit + combine for nb permutations; bf_out[g * ld + col0 + b]; jp_out (nullable, device):
+    // the chunk's jointPosterior terms go to jp_out[(g * ld + col0 + b) * sets + w]
+    void run_chunk_device_perms(cudaStream_t s, int nb, double* bf_out, long long ld, int col0, double* jp_out = nullptr) {
         if (ngenes == 0 || nb == 0) return;
+        const int sets = adjusted ? 3 : 2;
         Timed tr;
         if (time_kernels) tr = tick_begin(1, s);
+        bool with_jit = false;
         {
-            static const MrgDecim dc = decimation_by_32();
             const int ib = (int)idx_bytes();
-            const size_t per_warp = permgen_smem_per_warp(max_n, ib);
             const size_t cap = 200 * 1024;
-            if (per_warp <= cap) {
-                int wpb = (int)std::max<size_t>(1, std::min<size_t>(4, cap / per_warp));
-                size_t smem = per_warp * wpb;
-                int grid = std::min((ngenes + wpb - 1) / wpb, n_sm * std::max(1, std::min(16, (int)(cap / smem))));
-                if (wide_idx) {
-                    CK(cudaFuncSetAttribute(permgen_warp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    permgen_warp_kernel<uint32_t><<<grid, wpb * 32, smem, s>>>(d_off.p, ngenes, d_seeds.p, (uint32_t*)d_perm.p, nb, dc, max_n);
-                } else {
-                    CK(cudaFuncSetAttribute(permgen_warp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    permgen_warp_kernel<uint16_t><<<grid, wpb * 32, smem, s>>>(d_off.p, ngenes, d_seeds.p, (uint16_t*)d_perm.p, nb, dc, max_n);
-                }
+            if (permgen_smem_per_group(max_n, ib, 32) <= cap) {
+                with_jit = true;
+                CK(cudaMemsetAsync(d_jit.p, 0xff, (size_t)ngenes * nb * sets * 6 * sizeof(uint32_t), s));
+                PermgenArgs pa;
+                std::memset(&pa, 0, sizeof(pa));
+                pa.off = d_off.p; pa.ngenes = ngenes; pa.seeds = d_seeds.p; pa.seed_mode = seed_mode; pa.perm_b0 = perms_done;
+                pa.perm_out = d_perm.p; pa.nb = nb; pa.nmax = max_n;
+                pa.vals = adjusted ? d_resid.p : d_logy.p; pa.fitted = adjusted ? d_fitted.p : nullptr;
+                pa.part = d_part.p; pa.n1 = d_n1.p; pa.sets = sets; pa.jit_state = d_jit.p;
+                const int gs = pick_group_size();
+                if (wide_idx) launch_permgen<uint32_t>(s, pa, gs);
+                else launch_permgen<uint16_t>(s, pa, gs);
             } else {
                 // genes too long for the shared-memory Fisher-Yates array: thread-per-gene kernel, global scratch
+                // (per-gene streams only; constant subsets are not jittered on this path and fail as "constant")
+                if (seed_mode != 0) throw ScddError{SCDD_ERR_TOO_LARGE, "per-permutation streams need genes that fit shared memory"};
                 const int tpb = 64;
                 if (wide_idx)
                     permgen_kernel<uint32_t><<<(ngenes + tpb - 1) / tpb, tpb, 0, s>>>(d_off.p, ngenes, d_seeds.p,
@@ -442,15 +497,17 @@ struct Pipeline {
         a.perm_kind = wide_idx ? PERM_U32 : PERM_U16;
         a.perm_b0 = 0;
         a.nb = nb;
-        a.sets = adjusted ? 3 : 2;
+        a.sets = sets;
         a.jp = d_jp.p;
+        a.jit_state = with_jit ? d_jit.p : nullptr;
         const bool measure = !have_order && ngenes >= 2 * n_sm;   // worth ordering only when genes outnumber the SMs
         if (measure) { begin_cost_measurement(s); a.gene_cost = d_gene_cost.p; }
         launch_fit(s, a, adjusted ? max_n : max_half);
         if (measure) finish_cost_measurement(s);
         const long long units = (long long)ngenes * nb;
-        combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(d_jp.p, ngenes, nb, a.sets, bf_out, ld, col0);
+        combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(d_jp.p, ngenes, nb, a.sets, bf_out, ld, col0, jp_out);
         CK(cudaGetLastError());
+        perms_done += nb;
     }
 
     void read_stats(scdd_stats* st, cudaStream_t s) {
@@ -480,7 +537,10 @@ struct Shard {
 };
 
 static std::vector<int> active_devices() {
-    if (!g_devices.empty()) return g_devices;
+    {
+        std::lock_guard<std::mutex> lk(g_devices_mu);
+        if (!g_devices.empty()) return g_devices;
+    }
     int cur = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
     return std::vector<int>{cur};
@@ -504,30 +564,6 @@ static int guarded(F&& f) {
     }
 }
 
-// splits genes over devices; single-device calls alias the caller's arrays (no copy)
-static void make_shards(const std::vector<int>& devs, const int64_t* gene_off, int ngenes,
-                        std::vector<std::vector<int>>& assign) {
-    assign.assign(devs.size(), {});
-    if (devs.size() == 1) {
-        assign[0].resize(ngenes);
-        std::iota(assign[0].begin(), assign[0].end(), 0);
-        return;
-    }
-    std::vector<int> order(ngenes);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        return (gene_off[x + 1] - gene_off[x]) > (gene_off[y + 1] - gene_off[y]);
-    });
-    std::vector<double> load(devs.size(), 0.0);
-    for (int g : order) {
-        size_t best = 0;
-        for (size_t d = 1; d < devs.size(); d++) if (load[d] < load[best]) best = d;
-        assign[best].push_back(g);
-        load[best] += (double)(gene_off[g + 1] - gene_off[g]);
-    }
-    for (auto& v : assign) std::sort(v.begin(), v.end());
-}
-
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -545,6 +581,7 @@ int32_t scdd_set_devices(const int32_t* devices, int32_t n) {
         if (devices[i] < 0 || devices[i] >= cnt) return fail(SCDD_ERR_NO_DEVICE, "device index out of range");
         v.push_back(devices[i]);
     }
+    std::lock_guard<std::mutex> lk(g_devices_mu);
     g_devices = v;
     return SCDD_OK;
 }
@@ -641,31 +678,74 @@ int32_t scdd_fit_observed(const double* logy, const int64_t* gene_off, const int
 }
 
 // ---------------------------------------------------------------- permutations
-struct PermJob {
-    int dev;
-    std::vector<int> genes;
+// One cached pipeline (device buffers + stream + pinned staging) per device: a call reuses the previous call's
+// allocations, so the end-to-end cost of scdd_perm_bf is copies + kernels, not cudaMalloc/cudaFree of gigabytes.
+// scdd_release_cache() frees them.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes <= cap) return p;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+        return p;
+    }
+    void release() { if (p) { cudaFreeHost(p); p = nullptr; cap = 0; } }
 };
-
-// One cached pipeline (device buffers + stream) per device: a call reuses the previous call's allocations, so the
-// end-to-end cost of scdd_perm_bf is copies + kernels, not cudaMalloc/cudaFree of gigabytes.
 struct CachedPipeline {
     std::mutex mu;
     std::unique_ptr<Pipeline> P;
     cudaStream_t s = nullptr;
 };
+// pinned staging of one gene shard of a multi-device call (logy, cond, cdr, seeds, results); kept per shard SLOT, not
+// per device, so that a device may be listed twice (two shards on one GPU: how the sharded path is tested on one GPU)
+struct ShardStage { PinnedBuf stage[5]; };
+static std::mutex g_stage_mu;
+static std::vector<std::unique_ptr<ShardStage>> g_stage;
+static ShardStage& shard_stage(size_t slot) {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    while (g_stage.size() <= slot) g_stage.emplace_back(new ShardStage());
+    return *g_stage[slot];
+}
+static std::mutex g_cache_mu;
+static std::map<int, std::unique_ptr<CachedPipeline>> g_cache;
 static CachedPipeline& cached_pipeline(int dev) {
-    static std::mutex g;
-    static std::map<int, std::unique_ptr<CachedPipeline>> m;
-    std::lock_guard<std::mutex> lk(g);
-    auto& e = m[dev];
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto& e = g_cache[dev];
     if (!e) e.reset(new CachedPipeline());
     return *e;
 }
 
-static void perm_bf_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng, int B,
-                        const int32_t* perm_idx, const uint32_t* seed6, const double* cdr, const scdd_cfg* cfg,
-                        double* bf_perm, uint32_t* seed6_out, scdd_stats* st) {
-    if (ng == 0 || B == 0) return;
+typedef int32_t (*scdd_interrupt_fn)(void*);
+struct PermCall {
+    int B = 0;              // permutations of the whole call = row stride of bf_perm / jp_terms
+    int b0 = 0, nbp = 0;    // this invocation computes permutations [b0, b0 + nbp)
+    const int32_t* perm_idx = nullptr;
+    const uint32_t* seed6 = nullptr;
+    int seed_mode = 0;
+    const double* cdr = nullptr;
+    const scdd_cfg* cfg = nullptr;
+    double* bf_perm = nullptr;      // [ng * B]
+    double* jp_terms = nullptr;     // nullable [ng * B * sets]
+    uint32_t* seed6_out = nullptr;  // nullable [ng * 6] (seed_mode 0)
+    double* gene_cost = nullptr;    // nullable [ng]: EM work per gene measured on the first chunk
+};
+
+// Interruption: opts->interrupt is polled between permutation chunks, always on the CALLING thread (R's API is
+// main-thread only: the glue's callback wraps R_CheckUserInterrupt in R_ToplevelExec).  Worker threads of a
+// multi-device call only read the shared `cancel` flag.
+static void perm_bf_one(int dev, const double* logy, const int64_t* off, const int32_t* cond, int ng,
+                        const PermCall& pc, scdd_stats* st, scdd_interrupt_fn intr, void* intr_arg,
+                        std::atomic<int>* cancel = nullptr) {
+    const int B = pc.B;
+    auto cancelled = [&]() {
+        if (cancel && cancel->load()) return true;
+        if (intr && intr(intr_arg)) { if (cancel) cancel->store(1); return true; }
+        return false;
+    };
+    const bool polls = intr != nullptr || cancel != nullptr;
+    if (ng == 0 || pc.nbp == 0) return;
     CachedPipeline& C = cached_pipeline(dev);
     std::lock_guard<std::mutex> lk(C.mu);
     CK(cudaSetDevice(dev));
@@ -677,55 +757,76 @@ static void perm_bf_one(int dev, const double* logy, const int64_t* off, const i
         cudaEvent_t t0, t1;
         CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
         CK(cudaEventRecord(t0, s));
-        P.upload(dev, logy, off, cond, ng, cfg, cdr, s);
-        P.d_bf.alloc((size_t)ng * B);
+        P.upload(dev, logy, off, cond, ng, pc.cfg, pc.cdr, s);
         const int sets = P.adjusted ? 3 : 2;
+        const int nbp = pc.nbp;
+        P.d_bf.alloc((size_t)ng * nbp);
+        DevBuf<double> d_terms;
+        if (pc.jp_terms) d_terms.alloc((size_t)ng * nbp * sets);
         const int64_t base = off[0];
-        double h2d = (double)P.nnz * 12 + (ng + 1) * 8.0 + (cdr ? P.nnz * 8.0 : 0.0);
-        if (perm_idx) {
+        double h2d = (double)P.nnz * 12 + (ng + 1) * 8.0 + (pc.cdr ? P.nnz * 8.0 : 0.0);
+        bool interrupted = false;
+        if (pc.perm_idx) {
             // host-drawn permutations (the R shim's own sample() calls): whole table resident
             const size_t cnt = P.nnz * (size_t)B;
             DevBuf<int32_t> d_pi;
             d_pi.alloc(cnt);
-            CK(cudaMemcpyAsync(d_pi.p, perm_idx + (size_t)base * B, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_pi.p, pc.perm_idx + (size_t)base * B, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, s));
             h2d += cnt * 4.0;
             // jp chunked over permutations to bound memory
-            int bc = (int)std::max<long long>(1, std::min<long long>(B, (1LL << 27) / std::max(1, ng * sets)));
+            int bc = (int)std::max<long long>(1, std::min<long long>(nbp, (1LL << 27) / std::max(1, ng * sets)));
             P.d_jp.alloc((size_t)ng * bc * sets);
-            for (int b0 = 0; b0 < B; b0 += bc) {
-                int nb = std::min(bc, B - b0);
+            for (int c0 = 0; c0 < nbp && !interrupted; c0 += bc) {
+                int nb = std::min(bc, nbp - c0);
                 FitArgs a = P.base_args();
-                a.perm = d_pi.p; a.perm_bstride = B; a.perm_kind = PERM_I32_1BASED; a.perm_b0 = b0;
+                a.perm = d_pi.p; a.perm_bstride = B; a.perm_kind = PERM_I32_1BASED; a.perm_b0 = pc.b0 + c0;
                 a.nb = nb; a.sets = sets; a.jp = P.d_jp.p;
                 P.launch_fit(s, a, P.adjusted ? P.max_n : P.max_half);
                 const long long units = (long long)ng * nb;
-                combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(P.d_jp.p, ng, nb, sets, P.d_bf.p, B, b0);
+                combine_kernel<<<(int)((units + 255) / 256), 256, 0, s>>>(P.d_jp.p, ng, nb, sets, P.d_bf.p, nbp, c0, d_terms.p);
                 CK(cudaGetLastError());
+                if (polls) { CK(cudaStreamSynchronize(s)); if (cancelled()) interrupted = true; }
             }
             CK(cudaStreamSynchronize(s));
         } else {
             // device-drawn permutations, chunked so the index buffer stays below ~2 GiB
             long long per_perm = (long long)P.nnz * (long long)P.idx_bytes();
-            int bc = (int)std::max<long long>(1, std::min<long long>(B, (2LL << 30) / std::max<long long>(1, per_perm)));
+            int bc = (int)std::max<long long>(1, std::min<long long>(nbp, (2LL << 30) / std::max<long long>(1, per_perm)));
             bc = (int)std::min<long long>(bc, std::max<long long>(1, (1LL << 27) / std::max(1, ng * sets)));
-            P.alloc_perm_chunk(bc, seed6, s);
-            h2d += ng * 24.0;
-            for (int b0 = 0; b0 < B; b0 += bc) {
-                int nb = std::min(bc, B - b0);
-                P.run_chunk_device_perms(s, nb, P.d_bf.p, B, b0);
+            if (polls || pc.gene_cost) bc = std::min(bc, 16);   // interruptible calls / cost probes: chunks of <= 16 permutations
+            P.alloc_perm_chunk(bc, pc.seed6, s, pc.seed_mode, pc.seed_mode ? B : ng);
+            P.perms_done = pc.seed_mode ? pc.b0 : 0;
+            h2d += (pc.seed_mode ? B : ng) * 24.0;
+            for (int c0 = 0; c0 < nbp && !interrupted; c0 += bc) {
+                int nb = std::min(bc, nbp - c0);
+                P.run_chunk_device_perms(s, nb, P.d_bf.p, nbp, c0, d_terms.p);
+                if (polls) { CK(cudaStreamSynchronize(s)); if (cancelled()) interrupted = true; }
             }
-            if (seed6_out)
-                CK(cudaMemcpyAsync(seed6_out, P.d_seeds.p, (size_t)ng * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (pc.seed6_out && pc.seed_mode == 0)
+                CK(cudaMemcpyAsync(pc.seed6_out, P.d_seeds.p, (size_t)ng * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (pc.gene_cost) {
+                if (P.have_order && P.d_gene_cost.n >= (size_t)ng)
+                    CK(cudaMemcpyAsync(pc.gene_cost, P.d_gene_cost.p, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, s));
+                else
+                    for (int g = 0; g < ng; g++) pc.gene_cost[g] = (double)(off[g + 1] - off[g]);
+            }
         }
-        CK(cudaMemcpyAsync(bf_perm, P.d_bf.p, (size_t)ng * B * sizeof(double), cudaMemcpyDeviceToHost, s));
+        // results: rows of nbp values into the caller's rows of B values
+        CK(cudaMemcpy2DAsync(pc.bf_perm + pc.b0, (size_t)B * sizeof(double), P.d_bf.p, (size_t)nbp * sizeof(double),
+                             (size_t)nbp * sizeof(double), (size_t)ng, cudaMemcpyDeviceToHost, s));
+        if (pc.jp_terms)
+            CK(cudaMemcpy2DAsync(pc.jp_terms + (size_t)pc.b0 * sets, (size_t)B * sets * sizeof(double), d_terms.p,
+                                 (size_t)nbp * sets * sizeof(double), (size_t)nbp * sets * sizeof(double), (size_t)ng,
+                                 cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(t1, s));
         P.read_stats(st, s);
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, t0, t1));
-        st->total_ms = std::max<double>(st->total_ms, ms);
+        st->total_ms += ms;
         st->h2d_bytes += h2d;
-        st->d2h_bytes += (double)ng * B * 8.0;
+        st->d2h_bytes += (double)ng * nbp * 8.0 * (pc.jp_terms ? 1 + sets : 1);
         cudaEventDestroy(t0); cudaEventDestroy(t1);
+        if (interrupted) throw ScddError{SCDD_ERR_INTERRUPTED, "interrupted by the caller between permutation chunks"};
     } catch (...) {
         cudaStreamSynchronize(s);
         cudaGetLastError();
@@ -733,80 +834,191 @@ static void perm_bf_one(int dev, const double* logy, const int64_t* off, const i
     }
 }
 
-int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
-                     int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
-                     const scdd_cfg* cfg, double* bf_perm, uint32_t* seed6_out, scdd_stats* stats) {
+// adds the counters of one shard / phase; device times of concurrent shards overlap, so total_ms is handled by the caller
+static void merge_stats(scdd_stats& dst, const scdd_stats& src) {
+    const double* a = reinterpret_cast<const double*>(&src);
+    double* d = reinterpret_cast<double*>(&dst);
+    const double keep = dst.total_ms;
+    for (size_t k = 0; k < sizeof(scdd_stats) / sizeof(double); k++) d[k] += a[k];
+    dst.total_ms = keep;
+}
+
+// Multi-device call: each device's genes are gathered into PINNED staging (one pass over the caller's pageable arrays,
+// then full-speed asynchronous H2D), the shards run concurrently on one host thread per device, results are scattered
+// back.  Two phases for device-drawn permutations: a short first phase on shards balanced by the number of nonzero
+// cells measures the EM work of every gene (it is a property of the gene, not of the permutation); the remaining
+// permutations run on shards re-dealt longest-first by that MEASURED cost, every gene's stream continuing from the
+// state the first phase left (balance by cell counts alone leaves the slowest of eight devices ~6 % behind).
+static void perm_bf_sharded(const std::vector<int>& devs, const double* logy, const int64_t* gene_off,
+                            const int32_t* cond01, int ngenes, const PermCall& call, scdd_stats& st,
+                            scdd_interrupt_fn intr, void* intr_arg) {
+    const int B = call.B;
+    const int sets = call.cdr ? 3 : 2;
+    const bool device_perms = call.perm_idx == nullptr;
+    std::vector<uint32_t> seeds_cur;          // per-gene stream states carried between the phases (seed_mode 0)
+    if (device_perms && call.seed_mode == 0) seeds_cur.assign(call.seed6, call.seed6 + (size_t)ngenes * 6);
+    std::vector<double> cost(ngenes);
+    for (int g = 0; g < ngenes; g++) cost[g] = (double)(gene_off[g + 1] - gene_off[g]);
+    const int probe = (device_perms && B > 32 && ngenes >= 4 * (int)devs.size()) ? 8 : 0;   // phase-1 permutations
+    struct Phase { int b0, nbp; bool measure; };
+    std::vector<Phase> phases;
+    if (probe) { phases.push_back({0, probe, true}); phases.push_back({probe, B - probe, false}); }
+    else phases.push_back({0, B, false});
+    double total_ms = 0.0;
+    std::atomic<int> cancel(0);
+    for (const Phase& ph : phases) {
+        // longest-processing-time-first deal of the genes by the current cost estimate
+        std::vector<std::vector<int>> assign(devs.size());
+        {
+            std::vector<int> order(ngenes);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+            std::vector<double> load(devs.size(), 0.0);
+            for (int g : order) {
+                size_t best = 0;
+                for (size_t d = 1; d < devs.size(); d++) if (load[d] < load[best]) best = d;
+                assign[best].push_back(g);
+                load[best] += cost[g];
+            }
+            for (auto& v : assign) std::sort(v.begin(), v.end());
+        }
+        std::vector<scdd_stats> sts(devs.size());
+        std::vector<ScddError> errs(devs.size(), ScddError{0, ""});
+        std::vector<std::thread> th;
+        std::atomic<int> running((int)devs.size());
+        for (size_t d = 0; d < devs.size(); d++) {
+            th.emplace_back([&, d]() {
+                std::memset(&sts[d], 0, sizeof(scdd_stats));
+                try {
+                    const std::vector<int>& gs = assign[d];
+                    const int ngl = (int)gs.size();
+                    if (ngl == 0) { running.fetch_sub(1); return; }
+                    CK(cudaSetDevice(devs[d]));
+                    ShardStage& C = shard_stage(d);
+                    std::vector<int64_t> off(ngl + 1, 0);
+                    for (int i = 0; i < ngl; i++) off[i + 1] = off[i] + (gene_off[gs[i] + 1] - gene_off[gs[i]]);
+                    const size_t nz = (size_t)off[ngl];
+                    double* ly = (double*)C.stage[0].get(std::max<size_t>(8, nz * 8));
+                    int32_t* cc = (int32_t*)C.stage[1].get(std::max<size_t>(8, nz * 4));
+                    double* cd = call.cdr ? (double*)C.stage[2].get(std::max<size_t>(8, nz * 8)) : nullptr;
+                    uint32_t* sd = (uint32_t*)C.stage[3].get((size_t)std::max(ngl, B) * 6 * 4 * 2);
+                    uint32_t* sdo = sd + (size_t)std::max(ngl, B) * 6;
+                    const size_t out_cnt = (size_t)ngl * ph.nbp;
+                    double* out = (double*)C.stage[4].get((out_cnt * (call.jp_terms ? 1 + sets : 1) + ngl) * 8);
+                    double* terms = call.jp_terms ? out + out_cnt : nullptr;
+                    double* gcost = out + out_cnt * (call.jp_terms ? 1 + sets : 1);
+                    std::vector<int32_t> pi;
+                    if (call.perm_idx) pi.resize(nz * (size_t)B);
+                    for (int i = 0; i < ngl; i++) {
+                        const int g = gs[i];
+                        const size_t o = (size_t)gene_off[g], n = (size_t)(gene_off[g + 1] - gene_off[g]);
+                        std::memcpy(ly + off[i], logy + o, n * 8);
+                        std::memcpy(cc + off[i], cond01 + o, n * 4);
+                        if (cd) std::memcpy(cd + off[i], call.cdr + o, n * 8);
+                        if (call.perm_idx) std::memcpy(&pi[(size_t)off[i] * B], call.perm_idx + o * (size_t)B, n * (size_t)B * 4);
+                        if (device_perms && call.seed_mode == 0) std::memcpy(sd + (size_t)i * 6, &seeds_cur[(size_t)g * 6], 24);
+                    }
+                    if (device_perms && call.seed_mode == 1) std::memcpy(sd, call.seed6, (size_t)B * 24);
+                    PermCall pc = call;
+                    pc.B = ph.nbp; pc.b0 = 0; pc.nbp = ph.nbp;       // the shard's own result block has ph.nbp columns
+                    pc.perm_idx = call.perm_idx ? pi.data() : nullptr;
+                    pc.seed6 = device_perms ? sd : nullptr;
+                    pc.cdr = cd;
+                    pc.bf_perm = out; pc.jp_terms = terms;
+                    pc.seed6_out = (device_perms && call.seed_mode == 0) ? sdo : nullptr;
+                    pc.gene_cost = ph.measure ? gcost : nullptr;
+                    if (device_perms && call.seed_mode == 1) pc.seed6 = sd + (size_t)ph.b0 * 6;   // this phase's streams
+                    perm_bf_one(devs[d], ly, off.data(), cc, ngl, pc, &sts[d], nullptr, nullptr, intr ? &cancel : nullptr);
+                    for (int i = 0; i < ngl; i++) {
+                        const int g = gs[i];
+                        std::memcpy(call.bf_perm + (size_t)g * B + ph.b0, out + (size_t)i * ph.nbp, (size_t)ph.nbp * 8);
+                        if (terms)
+                            std::memcpy(call.jp_terms + ((size_t)g * B + ph.b0) * sets, terms + (size_t)i * ph.nbp * sets,
+                                        (size_t)ph.nbp * sets * 8);
+                        if (pc.seed6_out) std::memcpy(&seeds_cur[(size_t)g * 6], sdo + (size_t)i * 6, 24);
+                        if (ph.measure) cost[g] = gcost[i];
+                    }
+                } catch (const ScddError& e) {
+                    errs[d] = e;
+                } catch (const std::exception& e) {
+                    errs[d] = ScddError{SCDD_ERR_CUDA, e.what()};
+                }
+                running.fetch_sub(1);
+            });
+        }
+        // the calling thread polls the caller's interrupt hook while the shards run
+        while (intr && running.load() > 0) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+            if (!cancel.load() && intr(intr_arg)) cancel.store(1);
+        }
+        for (auto& t : th) t.join();
+        for (auto& e : errs) if (e.code) throw e;
+        double phase_ms = 0.0;
+        for (auto& s1 : sts) { merge_stats(st, s1); phase_ms = std::max(phase_ms, s1.total_ms); }
+        total_ms += phase_ms;     // shards run concurrently: the phase lasts as long as its slowest device
+    }
+    st.total_ms = total_ms;
+    if (call.seed6_out && device_perms && call.seed_mode == 0)
+        std::memcpy(call.seed6_out, seeds_cur.data(), (size_t)ngenes * 24);
+}
+
+static int32_t perm_bf_entry(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                             int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                             const scdd_cfg* cfg, const scdd_perm_opts* opts, double* bf_perm, uint32_t* seed6_out,
+                             scdd_stats* stats) {
     int rc = check_common(logy, gene_off, cond01, ngenes, cfg);
     if (rc) return rc;
     if (B < 0 || (ngenes > 0 && B > 0 && !bf_perm)) return fail(SCDD_ERR_BAD_ARG, "bad B / null output");
     if ((perm_idx != nullptr) == (seed6 != nullptr) && ngenes > 0 && B > 0)
         return fail(SCDD_ERR_BAD_ARG, "give exactly one of perm_idx (host-drawn) or seed6 (device-drawn)");
+    const int seed_mode = opts ? opts->seed_mode : 0;
+    if (seed_mode != 0 && seed_mode != 1) return fail(SCDD_ERR_BAD_ARG, "seed_mode must be 0 (per gene) or 1 (per permutation)");
+    if (seed_mode == 1 && !seed6 && ngenes > 0 && B > 0) return fail(SCDD_ERR_BAD_ARG, "per-permutation streams need seed6");
     scdd_stats st;
     std::memset(&st, 0, sizeof(st));
     return guarded([&]() -> int {
         std::vector<int> devs = active_devices();
-        std::vector<std::vector<int>> assign;
-        make_shards(devs, gene_off, ngenes, assign);
-        if (devs.size() == 1) {
-            perm_bf_one(devs[0], logy, gene_off, cond01, ngenes, B, perm_idx, seed6, cdr, cfg, bf_perm, seed6_out, &st);
-        } else {
-            // gather each device's genes into a private CSR block, run the shards concurrently, scatter back
-            std::vector<scdd_stats> sts(devs.size());
-            std::vector<ScddError> errs(devs.size(), ScddError{0, ""});
-            std::vector<std::thread> th;
-            for (size_t d = 0; d < devs.size(); d++) {
-                th.emplace_back([&, d]() {
-                    std::memset(&sts[d], 0, sizeof(scdd_stats));
-                    try {
-                        const std::vector<int>& gs = assign[d];
-                        const int ngl = (int)gs.size();
-                        if (ngl == 0) return;
-                        std::vector<int64_t> off(ngl + 1, 0);
-                        for (int i = 0; i < ngl; i++) off[i + 1] = off[i] + (gene_off[gs[i] + 1] - gene_off[gs[i]]);
-                        const size_t nz = (size_t)off[ngl];
-                        std::vector<double> ly(nz), cd;
-                        std::vector<int32_t> cc(nz), pi;
-                        std::vector<uint32_t> sd, sdo;
-                        if (cdr) cd.resize(nz);
-                        if (perm_idx) pi.resize(nz * (size_t)B);
-                        if (seed6) { sd.resize((size_t)ngl * 6); sdo.resize((size_t)ngl * 6); }
-                        for (int i = 0; i < ngl; i++) {
-                            const int g = gs[i];
-                            const size_t o = (size_t)gene_off[g], n = (size_t)(gene_off[g + 1] - gene_off[g]);
-                            std::memcpy(&ly[off[i]], logy + o, n * 8);
-                            std::memcpy(&cc[off[i]], cond01 + o, n * 4);
-                            if (cdr) std::memcpy(&cd[off[i]], cdr + o, n * 8);
-                            if (perm_idx) std::memcpy(&pi[(size_t)off[i] * B], perm_idx + o * (size_t)B, n * (size_t)B * 4);
-                            if (seed6) std::memcpy(&sd[(size_t)i * 6], seed6 + (size_t)g * 6, 24);
-                        }
-                        std::vector<double> out((size_t)ngl * B);
-                        perm_bf_one(devs[d], ly.data(), off.data(), cc.data(), ngl, B, perm_idx ? pi.data() : nullptr,
-                                    seed6 ? sd.data() : nullptr, cdr ? cd.data() : nullptr, cfg, out.data(),
-                                    seed6_out ? sdo.data() : nullptr, &sts[d]);
-                        for (int i = 0; i < ngl; i++) {
-                            std::memcpy(bf_perm + (size_t)gs[i] * B, &out[(size_t)i * B], (size_t)B * 8);
-                            if (seed6_out) std::memcpy(seed6_out + (size_t)gs[i] * 6, &sdo[(size_t)i * 6], 24);
-                        }
-                    } catch (const ScddError& e) {
-                        errs[d] = e;
-                    } catch (const std::exception& e) {
-                        errs[d] = ScddError{SCDD_ERR_CUDA, e.what()};
-                    }
-                });
-            }
-            for (auto& t : th) t.join();
-            for (auto& e : errs) if (e.code) throw e;
-            for (auto& s1 : sts) {
-                const double* src = reinterpret_cast<const double*>(&s1);
-                double* dst = reinterpret_cast<double*>(&st);
-                for (size_t k = 0; k < sizeof(scdd_stats) / sizeof(double); k++) dst[k] += src[k];
-                st.total_ms = std::max(st.total_ms, s1.total_ms);
-            }
+        PermCall call;
+        call.B = B; call.b0 = 0; call.nbp = B;
+        call.perm_idx = perm_idx; call.seed6 = seed6; call.seed_mode = seed_mode; call.cdr = cdr; call.cfg = cfg;
+        call.bf_perm = bf_perm; call.jp_terms = opts ? opts->jp_terms : nullptr; call.seed6_out = seed6_out;
+        scdd_interrupt_fn intr = opts ? opts->interrupt : nullptr;
+        void* intr_arg = opts ? opts->interrupt_arg : nullptr;
+        if (ngenes > 0 && B > 0) {
+            if (devs.size() == 1) perm_bf_one(devs[0], logy, gene_off, cond01, ngenes, call, &st, intr, intr_arg);
+            else perm_bf_sharded(devs, logy, gene_off, cond01, ngenes, call, st, intr, intr_arg);
         }
         if (stats) *stats = st;
         if (st.failed_sets > 0) return fail(SCDD_ERR_FIT_FAILED, "some permuted fit-sets had no valid model; their bf_perm is NaN");
         return SCDD_OK;
     });
+}
+
+int32_t scdd_perm_bf(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                     int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                     const scdd_cfg* cfg, double* bf_perm, uint32_t* seed6_out, scdd_stats* stats) {
+    return perm_bf_entry(logy, gene_off, cond01, ngenes, B, perm_idx, seed6, cdr, cfg, nullptr, bf_perm, seed6_out, stats);
+}
+
+int32_t scdd_perm_bf_ex(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                        int32_t B, const int32_t* perm_idx, const uint32_t* seed6, const double* cdr,
+                        const scdd_cfg* cfg, const scdd_perm_opts* opts, double* bf_perm, uint32_t* seed6_out,
+                        scdd_stats* stats) {
+    return perm_bf_entry(logy, gene_off, cond01, ngenes, B, perm_idx, seed6, cdr, cfg, opts, bf_perm, seed6_out, stats);
+}
+
+void scdd_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& kv : g_cache) {
+        CachedPipeline& C = *kv.second;
+        std::lock_guard<std::mutex> l2(C.mu);
+        if (cudaSetDevice(kv.first) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (C.s) cudaStreamSynchronize(C.s);
+        C.P.reset();
+        if (C.s) { cudaStreamDestroy(C.s); C.s = nullptr; }
+    }
+    std::lock_guard<std::mutex> l3(g_stage_mu);
+    for (auto& sp : g_stage) for (auto& b : sp->stage) b.release();
 }
 
 // ---------------------------------------------------------------- KS

@@ -139,8 +139,12 @@ def fit_observed(logy, cond01, gene_off, cfg=None, with_bf=True, allow_failed=Fa
 
 
 def perm_bf(logy, cond01, gene_off, B, perm_idx=None, seed6=None, cdr=None, cfg=None, allow_failed=False,
-            return_seeds=False):
-    """Bayes-factor numerators of B permutations per gene: array [ngenes, B] (+ stats dict)."""
+            return_seeds=False, seed_mode=0, return_terms=False, interrupt=None):
+    """Bayes-factor numerators of B permutations per gene: array [ngenes, B] (+ stats dict).
+
+    seed_mode 0: seed6 [ngenes, 6], one stream per gene (parallelBy "Genes"); 1: seed6 [B, 6], permutation b of every
+    gene from stream b (parallelBy "Permutations").  return_terms adds the jointPosterior terms [ngenes, B, sets]
+    (JP(c1), JP(c2)[, JP(oa)]) as the last return value.  interrupt: a callable polled between chunks (True = stop)."""
     cfg = cfg or make_cfg()
     logy, cond01, gene_off = _prep(logy, cond01, gene_off)
     ng = gene_off.size - 1
@@ -149,19 +153,35 @@ def perm_bf(logy, cond01, gene_off, B, perm_idx=None, seed6=None, cdr=None, cfg=
         perm_idx = np.ascontiguousarray(perm_idx, dtype=np.int32)
         assert perm_idx.size == gene_off[-1] * B
     if seed6 is not None:
-        seed6 = np.ascontiguousarray(seed6, dtype=np.uint32).reshape(ng, 6)
+        seed6 = np.ascontiguousarray(seed6, dtype=np.uint32).reshape(B if seed_mode else ng, 6)
     if cdr is not None:
         cdr = np.ascontiguousarray(cdr, dtype=np.float64)
         assert cdr.size == logy.size
     seeds_out = np.zeros((ng, 6), dtype=np.uint32) if (return_seeds and seed6 is not None) else None
+    terms = np.zeros((ng, B, 3 if cdr is not None else 2)) if return_terms else None
     st = Stats()
-    rc = _lib.lib().scdd_perm_bf(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, int(B),
-                                 _lib.ptr(perm_idx), _lib.ptr(seed6), _lib.ptr(cdr), C.byref(cfg),
-                                 out.ctypes.data, _lib.ptr(seeds_out), C.byref(st))
+    opts = _lib.PermOpts()
+    opts.seed_mode = int(seed_mode)
+    opts.jp_terms = _lib.ptr(terms)
+    hook = None
+    if interrupt is not None:
+        hook = _lib.INTERRUPT_FN(lambda _arg: 1 if interrupt() else 0)
+        opts.interrupt = hook
+    rc = _lib.lib().scdd_perm_bf_ex(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, int(B),
+                                    _lib.ptr(perm_idx), _lib.ptr(seed6), _lib.ptr(cdr), C.byref(cfg), C.byref(opts),
+                                    out.ctypes.data, _lib.ptr(seeds_out), C.byref(st))
     _lib.check(rc, allow=(_lib.ERR_FIT_FAILED,) if allow_failed else ())
+    ret = [out, st.as_dict()]
     if return_seeds:
-        return out, st.as_dict(), seeds_out
-    return out, st.as_dict()
+        ret.append(seeds_out)
+    if return_terms:
+        ret.append(terms)
+    return tuple(ret)
+
+
+def release_cache():
+    """frees the per-device buffers the library keeps between perm_bf calls (scdd_release_cache)"""
+    _lib.lib().scdd_release_cache()
 
 
 def ks(vals, cond01, gene_off, old_pvalue=False):

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_lib.EXPORTS) == names
-    assert L.scdd_abi_version() == 1
+    assert L.scdd_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -125,9 +125,12 @@ def test_perm_bf_adjusted_cdr(golden_dir):
     cdr = np.broadcast_to(C, X.shape)[X > 0]
     B = 6
     seeds = hp.gene_seeds(5, 10)
-    out, st = hp.perm_bf(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS))
-    ref = po.perm_batch(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
-    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-7)
+    out, st, terms = hp.perm_bf(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS), return_terms=True)
+    ref = po.perm_batch_ex(logy, c01, off, B, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
+    # each jointPosterior term at 1e-8; their difference JP(c1) + JP(c2) - JP(oa) cancels, so it is held to 1e-8 of the
+    # terms' magnitude (R/permutations.R:265-267)
+    np.testing.assert_allclose(terms, ref["jp_terms"], rtol=RTOL)
+    assert (np.abs(out - ref["bf_perm"]) <= RTOL * np.abs(ref["jp_terms"]).sum(axis=2)).all()
     assert st["fit_sets"] == 3 * 10 * B
 
 
@@ -284,9 +287,10 @@ def test_adjusted_path_larger_genes():
     rng = np.random.default_rng(4)
     cdr = 0.3 + 0.5 * rng.random(logy.size)
     seeds = hp.gene_seeds(8, 3)
-    out, st = hp.perm_bf(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS))
-    ref = po.perm_batch(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
-    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-6)
+    out, st, terms = hp.perm_bf(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=hp.make_cfg(**PRIORS), return_terms=True)
+    ref = po.perm_batch_ex(logy, c01, off, 3, seed6=seeds, cdr=cdr, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(terms, ref["jp_terms"], rtol=RTOL)
+    assert (np.abs(out - ref["bf_perm"]) <= RTOL * np.abs(ref["jp_terms"]).sum(axis=2)).all()
     assert st["fit_sets"] == 3 * 3 * 3
 
 
