@@ -73,55 +73,86 @@ def load_base_matrix():
     return X[:, cond == cond[0]]
 
 
+LOGFC_SD = 0.7   # spread of the binned observed log fold changes (findFC): DE genes move 1-3 of these
+
+
+def _gene_row(rng, cat, mom, n_per_cond, mode_fc):
+    """one gene of category `cat`: 2 * n_per_cond normalized counts (no continuity jitter yet)"""
+    m, v, zf = mom[rng.integers(mom.shape[0])]
+    f = mode_fc[rng.integers(len(mode_fc))]
+    fc2 = np.exp(f * np.sqrt(np.log(1.0 + v / (m * m))))
+    r1, p1 = _calc_rp(m, v)
+    r2, p2 = _calc_rp(m * fc2, v * fc2 * fc2)            # second mode: same CV, mean x FC2
+    nnz = max(3, int(round(n_per_cond * (1.0 - zf))))
+
+    def draw(w2, shift=1.0):
+        """nnz values: fraction w2 from the second mode; `shift` multiplies the first mode's mean"""
+        n2 = int(round(nnz * w2))
+        ra, pa = (r1, p1) if shift == 1.0 else _calc_rp(m * shift, v * shift * shift)
+        a = _ztnb(rng, ra, pa, nnz - n2)
+        b = _ztnb(rng, r2, p2, n2) if n2 else np.zeros(0)
+        return np.concatenate([a, b])
+
+    if cat == "EE":
+        v1, v2 = draw(0.0), draw(0.0)
+    elif cat == "DE":
+        fc = 2.0 ** (rng.uniform(1.0, 3.0) * LOGFC_SD * (1 if rng.random() < 0.5 else -1))
+        v1, v2 = draw(0.0), draw(0.0, shift=fc)
+    elif cat == "DP":
+        w = (0.33, 0.66) if rng.random() < 0.5 else (0.66, 0.33)
+        v1, v2 = draw(w[0]), draw(w[1])
+    elif cat == "DM":
+        v1, v2 = draw(0.0), draw(0.5)
+        if rng.random() < 0.5:
+            v1, v2 = v2, v1
+    elif cat == "DB":
+        v1, v2 = draw(0.5), draw(0.0, shift=np.sqrt(fc2))
+        if rng.random() < 0.5:
+            v1, v2 = v2, v1
+    else:  # EP
+        v1, v2 = draw(0.5), draw(0.5)
+    row = np.empty(2 * n_per_cond)
+    row[:n_per_cond] = _place(rng, n_per_cond, v1)
+    row[n_per_cond:] = _place(rng, n_per_cond, v2)
+    return row
+
+
+def _categories(n_genes, mix=None):
+    mix = dict(DEFAULT_MIX if mix is None else mix)
+    tot = float(sum(mix.values()))
+    counts = {c: int(round(n_genes * mix.get(c, 0) / tot)) for c in CATS}
+    counts["EE"] += n_genes - sum(counts.values())
+    return np.concatenate([[c] * counts[c] for c in CATS])
+
+
+def simulate_gene_block(genes, n_genes_total=20000, n_per_cond=25000, seed=284, mode_fc=(2, 3, 4), mix=None, base=None):
+    """Rows `genes` (indices into an n_genes_total-gene data set) of a simulateSet-style matrix in which EVERY GENE HAS
+    ITS OWN RNG STREAM (seed, gene index): a rank of a sharded job can draw just its shard -- BASELINE config 5 is
+    20,000 x 50,000 = 8 GB dense, which no rank needs to hold.  Returns (normcounts [len(genes), 2*n_per_cond], condition)."""
+    base = load_base_matrix() if base is None else base
+    mom = _base_moments(base)
+    cats = _categories(n_genes_total, mix)
+    genes = np.asarray(genes, dtype=np.int64)
+    X = np.empty((genes.size, 2 * n_per_cond))
+    for j, g in enumerate(genes):
+        rng = np.random.default_rng([int(seed), int(g)])
+        row = _gene_row(rng, cats[g], mom, n_per_cond, mode_fc)
+        nz = row != 0
+        row[nz] += rng.random(int(nz.sum()))
+        X[j] = row
+    return X, np.repeat([1, 2], n_per_cond)
+
+
 def simulate_set_style(n_genes=20000, n_per_cond=1000, seed=284, mode_fc=(2, 3, 4), mix=None, base=None,
                        return_categories=False):
     """Returns (normcounts [n_genes, 2*n_per_cond] float64, condition [2*n_per_cond] in {1,2})."""
     rng = np.random.default_rng(seed)
     base = load_base_matrix() if base is None else base
     mom = _base_moments(base)
-    mix = dict(DEFAULT_MIX if mix is None else mix)
-    tot = float(sum(mix.values()))
-    counts = {c: int(round(n_genes * mix.get(c, 0) / tot)) for c in CATS}
-    counts["EE"] += n_genes - sum(counts.values())
-    cats = np.concatenate([[c] * counts[c] for c in CATS])
+    cats = _categories(n_genes, mix)
     X = np.zeros((n_genes, 2 * n_per_cond))
-    logfc_sd = 0.7   # spread of the binned observed log fold changes (findFC): DE genes move 1-3 of these
     for i, cat in enumerate(cats):
-        m, v, zf = mom[rng.integers(mom.shape[0])]
-        f = mode_fc[rng.integers(len(mode_fc))]
-        fc2 = np.exp(f * np.sqrt(np.log(1.0 + v / (m * m))))
-        r1, p1 = _calc_rp(m, v)
-        r2, p2 = _calc_rp(m * fc2, v * fc2 * fc2)            # second mode: same CV, mean x FC2
-        nnz = max(3, int(round(n_per_cond * (1.0 - zf))))
-
-        def draw(w2, shift=1.0):
-            """nnz values: fraction w2 from the second mode; `shift` multiplies the first mode's mean"""
-            n2 = int(round(nnz * w2))
-            ra, pa = (r1, p1) if shift == 1.0 else _calc_rp(m * shift, v * shift * shift)
-            a = _ztnb(rng, ra, pa, nnz - n2)
-            b = _ztnb(rng, r2, p2, n2) if n2 else np.zeros(0)
-            return np.concatenate([a, b])
-
-        if cat == "EE":
-            v1, v2 = draw(0.0), draw(0.0)
-        elif cat == "DE":
-            fc = 2.0 ** (rng.uniform(1.0, 3.0) * logfc_sd * (1 if rng.random() < 0.5 else -1))
-            v1, v2 = draw(0.0), draw(0.0, shift=fc)
-        elif cat == "DP":
-            w = (0.33, 0.66) if rng.random() < 0.5 else (0.66, 0.33)
-            v1, v2 = draw(w[0]), draw(w[1])
-        elif cat == "DM":
-            v1, v2 = draw(0.0), draw(0.5)
-            if rng.random() < 0.5:
-                v1, v2 = v2, v1
-        elif cat == "DB":
-            v1, v2 = draw(0.5), draw(0.0, shift=np.sqrt(fc2))
-            if rng.random() < 0.5:
-                v1, v2 = v2, v1
-        else:  # EP
-            v1, v2 = draw(0.5), draw(0.5)
-        X[i, :n_per_cond] = _place(rng, n_per_cond, v1)
-        X[i, n_per_cond:] = _place(rng, n_per_cond, v2)
+        X[i] = _gene_row(rng, cat, mom, n_per_cond, mode_fc)
     nz = X != 0
     X[nz] += rng.random(int(nz.sum()))
     cond = np.repeat([1, 2], n_per_cond)
