@@ -228,6 +228,9 @@ int32_t scdd_selftest_x87_cumsum(const double* steps, int32_t n, double* out);
 int32_t scdd_selftest_exp(const double* x, int32_t n, double* out);
 /* softmax of G <= 5 log-terms exactly as the E-step evaluates it; logsumexp may be NULL */
 int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp);
+/* the kernels' table-driven logarithm (EM loop: log of the running product of softmax sums, log(pro^2 / sigsq)):
+ * out[i] = log(x[i]) for positive normal x */
+int32_t scdd_selftest_log(const double* x, int32_t n, double* out);
 /* the host-side tail of scdd_fedp: out[i] = 2 * pt(-|t[i]|, df[i]) */
 int32_t scdd_selftest_student_p(const double* t, const double* df, int32_t n, double* out);
 /* measured fp64 FMA throughput of the device (TFLOP/s, DFMA = 2 flop), used as the roofline denominator */

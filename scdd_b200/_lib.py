@@ -65,7 +65,7 @@ FIT_DTYPE = np.dtype([("G", np.int32), ("model_v", np.int32), ("n", np.int32), (
 EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set_devices", "scdd_default_cfg",
            "scdd_fit_observed", "scdd_perm_bf", "scdd_perm_bf_ex", "scdd_release_cache", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
-           "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax",
+           "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax", "scdd_selftest_log",
            "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
 
 
@@ -109,6 +109,7 @@ def lib():
     L.scdd_selftest_x87_cumsum.argtypes = [vp, C.c_int32, vp]
     L.scdd_selftest_exp.argtypes = [vp, C.c_int32, vp]
     L.scdd_selftest_softmax.argtypes = [vp, C.c_int32, vp, vp]
+    L.scdd_selftest_log.argtypes = [vp, C.c_int32, vp]
     L.scdd_measure_fp64_peak.argtypes = [C.c_int32, dp]
     L.scdd_measure_fp64_peak.restype = C.c_double
     i64 = C.c_int64

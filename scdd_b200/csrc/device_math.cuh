@@ -76,8 +76,10 @@ SCDD_HD double from_words(int hi, int lo) {
 }
 
 SCDD_HD double term_t(double a) { return fma(a, expc::L2E_T, expc::MAGIC); }
-// low word of t = N (two's complement) while |a| < 2^19; log-terms below -2^19 saturate
-SCDD_HD int term_n(double a, double t) { return ((unsigned)hi_word(a) >= 0xC1200000u) ? expc::NSAT : lo_word(t); }
+// low word of t = N (two's complement) while |N| < 2^31.  Log-terms a <= -2^18 saturate to NSAT = -2^30: every
+// unsaturated term has N = rint(a 2^11/ln2) > -2^18 * 2954.7 > -2^30, so a saturated ("minus infinity") term can
+// never out-rank a finite one in the integer max (round 1 saturated from -2^19, where N already reaches -1.5e9).
+SCDD_HD int term_n(double a, double t) { return ((unsigned)hi_word(a) >= 0xC1100000u) ? expc::NSAT : lo_word(t); }
 SCDD_HD double term_r(double a, double t) { return fma(t - expc::MAGIC, -expc::LN2_T, a); }
 SCDD_HD double term_s(double r) {
     using namespace expc;
@@ -91,6 +93,48 @@ SCDD_HD double term_e(double s, int n, int M, const double* tab) {
     const double T = tab[D & expc::TMASK];
     const double v = fma(T, s, T);
     return from_words(hi_word(v) + ((D >> expc::TB) << 20), lo_word(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// log(x) for positive NORMAL x, table driven (Tang): x = 2^E m, m in [1, 2); the top 8 fraction bits of m pick
+// c_j = 1 + (j + 1/2)/256; u = m rc_j - 1 (one fma, |u| <= 2^-9 + ulp) with rc_j = fl(1/c_j) and L_j = -log(rc_j)
+// tabulated in double from long double; log(x) = E ln2 + L_j + log1p(u), log1p by its series through u^5
+// (truncation u^6/6 < 1e-17).  ~1 ulp of the result; 9 fp64 + 8 other instructions, no branches.  The EM loop takes
+// two logarithms per iteration (the running product of the softmax sums, and log(pro^2 / sigsq) of the M-step):
+// CUDA's log() costs ~75 instructions per call with its range checks.
+// ---------------------------------------------------------------------------------------------
+#define SCDD_LOG_TABLE_SIZE 256
+struct LogTab { double rc, l; };
+
+inline const LogTab* log_table_host() {
+    static LogTab tab[SCDD_LOG_TABLE_SIZE];
+    static bool done = false;
+    if (!done) {
+        for (int j = 0; j < SCDD_LOG_TABLE_SIZE; j++) {
+            const long double c = 1.0L + ((long double)j + 0.5L) / (long double)SCDD_LOG_TABLE_SIZE;
+            tab[j].rc = (double)(1.0L / c);
+            tab[j].l = (double)(-logl((long double)tab[j].rc));
+        }
+        done = true;
+    }
+    return tab;
+}
+
+SCDD_HD double fast_log_core(double x, double rc, double l) {
+    const int hi = hi_word(x);
+    const double m = from_words((hi & 0x000fffff) | 0x3ff00000, lo_word(x));
+    const double u = fma(m, rc, -1.0);
+    double p = fma(u, 0.2, -0.25);
+    p = fma(p, u, 0.33333333333333331);
+    p = fma(p, u, -0.5);
+    p = p * u;
+    const double r = fma(u, p, u);
+    return fma((double)((hi >> 20) - 1023), 0.69314718055994529, l) + r;
+}
+SCDD_HD int fast_log_index(double x) { return (hi_word(x) >> 12) & (SCDD_LOG_TABLE_SIZE - 1); }
+SCDD_HD double fast_log_tab(double x, const LogTab* tab) {
+    const LogTab t = tab[fast_log_index(x)];
+    return fast_log_core(x, t.rc, t.l);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -138,6 +138,17 @@ __device__ double EXP_TABLE_GLOBAL[SCDD_EXP_TABLE_SIZE];   // source of the per-
 // The CTA's copy: a statically allocated shared array, so that every function (including the non-inlined E-step
 // dispatchers) addresses it as [index * 8 + link-time constant] with no base register and no address arithmetic.
 __shared__ double EXP_TABLE_SH[SCDD_EXP_TABLE_SIZE];
+// fast_log's table (device_math.cuh): 4 KB of static shared memory per CTA next to the exp table
+__device__ LogTab LOG_TABLE_GLOBAL[SCDD_LOG_TABLE_SIZE];
+__shared__ __align__(16) LogTab LOG_TABLE_SH[SCDD_LOG_TABLE_SIZE];
+__device__ __forceinline__ double fast_log(double x) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(LOG_TABLE_SH);
+    unsigned addr;
+    double rc, l;
+    asm("{ .reg .b32 j; bfe.u32 j, %1, 12, 8; mad.lo.u32 %0, j, 16, %2; }" : "=r"(addr) : "r"(__double2hiint(x)), "r"(base));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(l) : "r"(addr));
+    return fast_log_core(x, rc, l);
+}
 // constant-bank copies of device_math.cuh's expc:: constants (fetched with LDCU, no per-iteration immediates)
 __constant__ double EXP_TAB_CONST[3] = {2954.639443740597, -0.00033845077175778578, 1.0 / 6.0};
 
@@ -187,15 +198,28 @@ __device__ __forceinline__ double exp_table_sh(int D) {
     return T;
 }
 
+#ifndef SCDD_PIN_CONST_MAXG
+#define SCDD_PIN_CONST_MAXG 0       // G up to which the three exp constants are held in registers across the point loop
+#endif
 template <int G, bool GTAB = false>
 struct ParamsReg {
     double mu[G], nh[G], lc[G];
+    double kc[3];   // exp constants (only live when pinned; otherwise every use reads the constant bank)
+    static constexpr bool PIN = !GTAB && G <= SCDD_PIN_CONST_MAXG;
+    __device__ __forceinline__ double c(int i) const { return PIN ? kc[i] : EXP_TAB_CONST[i]; }
+    __device__ __forceinline__ void pin() {
+        if (PIN) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) asm volatile("ld.const.f64 %0, [%1];" : "=d"(kc[i]) : "l"(&EXP_TAB_CONST[i]));
+        }
+    }
     // 2^(j/2048): the CTA's shared copy, or (GTAB, label_of outside the fit loop) the global source
     __device__ __forceinline__ static double lookup(int D) { return GTAB ? EXP_TABLE_GLOBAL[D & expc::TMASK] : exp_table_sh(D); }
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
     __device__ __forceinline__ static double lookup(int D) { return exp_table_sh(D); }
+    __device__ __forceinline__ double c(int i) const { return EXP_TAB_CONST[i]; }
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
@@ -229,9 +253,12 @@ __device__ __forceinline__ int tree_imax(const int* v) {
 //   Outputs: e (U*G), d = x - mu, q = d^2, S = sum_k e_k and the integer shift M per point.
 // SAT = false drops the saturation test of term_n: legal when the caller has proved |t_k| < 2^19 for every point
 // (all variances above (data range)^2 / 2^20 -- see fit_row), which is the case for all but degenerate fits.
+// SAT: additionally, a point whose EVERY term is saturated (more than 2^18 log-units from all components) is redone
+// on a_k - max_k a_k, and that fp64 shift is returned in `far` for the log-likelihood (0 otherwise): the softmax is
+// exact in every regime, as mclust's own exp(t_k - max t) is.
 template <int G, int U, bool SAT, class P>
 __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm, double (&e)[U * G], double (&d)[U * G],
-                                             double (&q)[U * G], double (&S)[U], int (&M)[U]) {
+                                             double (&q)[U * G], double (&S)[U], int (&M)[U], double* far = nullptr) {
     using namespace expc;
     constexpr int N = U * G;
     double a[N], t[N], r[N], p[N], h[G], l[G];
@@ -251,17 +278,41 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         for (int k = 0; k < G; k++) a[u * G + k] = fma(q[u * G + k], h[k], l[k]);
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(a[i], EXP_TAB_CONST[0], MAGIC);                 // term_t
+    for (int i = 0; i < N; i++) t[i] = fma(a[i], prm.c(0), MAGIC);                 // term_t
 #pragma unroll
     for (int i = 0; i < N; i++) n[i] = SAT ? term_n(a[i], t[i]) : __double2loint(t[i]);
 #pragma unroll
     for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&n[u * G]);
+    if (SAT) {
 #pragma unroll
+        for (int u = 0; u < U; u++) {
+            double amax = 0.0;
+            if (M[u] == NSAT) {            // cold: every term saturated
+                amax = a[u * G];
+#pragma unroll
+                for (int k = 1; k < G; k++) amax = fmax(amax, a[u * G + k]);
+#pragma unroll
+                for (int k = 0; k < G; k++) {
+                    const int i = u * G + k;
+                    a[i] = __dsub_rn(a[i], amax);
+                    t[i] = fma(a[i], prm.c(0), MAGIC);
+                    n[i] = term_n(a[i], t[i]);
+                }
+                M[u] = tree_imax<G>(&n[u * G]);
+            }
+            if (far) far[u] = amax;
+        }
+    }
+#pragma unroll
+#ifdef SCDD_I2F_EXPERIMENT
+    for (int i = 0; i < N; i++) p[i] = SAT ? __dsub_rn(t[i], MAGIC) : (double)n[i];        // same value, conversion pipe
+#else
     for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
+#endif
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(p[i], EXP_TAB_CONST[1], a[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(p[i], prm.c(1), a[i]);
 #pragma unroll
-    for (int i = 0; i < N; i++) p[i] = fma(EXP_TAB_CONST[2], r[i], 0.5);                   // term_s
+    for (int i = 0; i < N; i++) p[i] = fma(prm.c(2), r[i], 0.5);                   // term_s
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
@@ -358,7 +409,9 @@ struct Team {
 //   mu = mu_old + S(z d)/S(z),  sigsq = S(z q)/S(z) - (S(z d)/S(z))^2
 // which equals mclust's two-pass update in exact arithmetic and needs no stored z matrix.
 // ---------------------------------------------------------------------------------------------
-// back half of a point: normalise the softmax terms and add the point to the M-step sums
+// back half of a point: normalise the softmax terms and add the point to the M-step sums.
+// sum_k z_k = 1 for every point (to rounding), so the weight of the LAST component is not accumulated: estep_pass
+// derives it as (points of this thread) - sum_{k < G-1} A_k, one DADD per point less.
 template <int G, int U>
 __device__ __forceinline__ void accumulate_back(const double (&e)[U * G], const double (&d)[U * G], const double (&q)[U * G],
                                                 const double (&S)[U], const int (&M)[U], double (&A)[G], double (&B)[G],
@@ -369,21 +422,32 @@ __device__ __forceinline__ void accumulate_back(const double (&e)[U * G], const 
 #pragma unroll
         for (int k = 0; k < G; k++) {
             double z = __dmul_rn(e[u * G + k], rs);
-            A[k] += z;
+            if (k < G - 1) A[k] += z;
             B[k] = fma(z, d[u * G + k], B[k]);
             C[k] = fma(z, q[u * G + k], C[k]);
         }
         pl *= S[u];      // sum_i log S_i is taken as the log of a running product (S in (0.97, 1.03 G])
+#ifdef SCDD_HS32_EXPERIMENT
+        hs = (long long)((int)hs + M[u]);
+#else
         hs += M[u];      // the shifts are integers: summed exactly, off the fp64 pipe
+#endif
     }
 }
 
 template <int G, int U, bool SAT, class P>
 __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
-                                                  double (&C)[G], double& pl, long long& hs) {
+                                                  double (&C)[G], double& pl, long long& hs, double& hfar) {
     double e[U * G], d[U * G], q[U * G], S[U];
     int M[U];
-    estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M);
+    if (SAT) {
+        double far[U];
+        estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M, far);
+#pragma unroll
+        for (int u = 0; u < U; u++) hfar += far[u];
+    } else {
+        estep_points<G, U, SAT, P>(x, prm, e, d, q, S, M);
+    }
     accumulate_back<G, U>(e, d, q, S, M, A, B, C, pl, hs);
 }
 
@@ -407,6 +471,7 @@ __device__ __forceinline__ auto load_params(const double* pm) {
         ParamsReg<G> p;
 #pragma unroll
         for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
+        p.pin();
         return p;
     }
 #else
@@ -417,15 +482,19 @@ __device__ __forceinline__ auto load_params(const double* pm) {
 #endif
 }
 
+#ifndef SCDD_LOOP_UNROLL
+#define SCDD_LOOP_UNROLL 1
+#endif
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            double (&v)[16]) {
     constexpr int NT = Team<TW>::NT;
+    constexpr int LOOP_UNROLL = SCDD_LOOP_UNROLL;
     const auto prm = load_params<G>(pm);
     double A[G], B[G], C[G];
 #pragma unroll
     for (int k = 0; k < G; k++) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
-    double hl = 0.0;
+    double hl = 0.0, hfar = 0.0;
     long long hs = 0;
     constexpr int CHUNK = 256 * NT;   // the running product is flushed every 256 points per thread (5^256 < DBL_MAX)
 #pragma unroll 1
@@ -435,23 +504,30 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         // pointer-bumped loops: the load is [register + immediate] and the bound test compares addresses
         const double* px = xs + base + Team<TW>::tid(lane);
         const double* const pend = xs + stop;
-#pragma unroll 1
+#pragma unroll LOOP_UNROLL
         for (; px + NT * (U - 1) < pend; px += NT * U) {
             double x[U];
 #pragma unroll
             for (int u = 0; u < U; u++) x[u] = px[NT * u];
-            accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hs);
+            accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hs, hfar);
         }
         if (U > 1) {
 #pragma unroll 1
             for (; px < pend; px += NT) {
                 double x[1] = {*px};
-                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hs);
+                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hs, hfar);
             }
         }
-        hl += log(pl);
+        hl += fast_log(pl);
     }
     hl = fma((double)hs, expc::LN2_T, hl);   // log-likelihood: sum_i log S_i + c sum_i M_i, the SAME c as in term_r
+    if (SAT) hl += hfar;
+    // weight of the last component from sum_k z_k = 1: this thread's point count minus the other weights
+    const int tid = Team<TW>::tid(lane);
+    double rest = (double)(tid < n ? (n - tid + NT - 1) / NT : 0);
+#pragma unroll
+    for (int k = 0; k < G - 1; k++) rest -= A[k];
+    A[G - 1] = rest;
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.0;
 #pragma unroll
@@ -488,7 +564,13 @@ __device__ __forceinline__ void label_pass(const double* __restrict__ xs, int n,
 #endif
 template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_MAXG) ? 2 : 1; };
 
-// returns the team total of slot (lane >> 1): the 16 partial sums never leave registers
+// same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code, kept out of line
+// so that it does not weigh on the register allocation of the EM loop
+// returns the team total of slot (lane >> 1): the 16 partial sums never leave registers.
+// ONE non-inlined function holds the point loops of all four G: ptxas then allocates for the widest (G = 5, 128
+// registers, callee-saved registers spilled once in the prologue) and every loop keeps its 64-bit accumulators in
+// aligned pairs.  One function per G (tried in round 2) is allocated tightly enough to avoid the prologue spill, and
+// pays for it with ~20 register moves per point inside the loop.
 template <int TW>
 __device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
                                               double* red) {
@@ -530,10 +612,65 @@ __device__ __noinline__ double label_dispatch(int G, const double* xs, int n, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Start of a G >= 2 row: mclust's qclass quantile classes and the first M-step from them (z = unmap(qclass)).
+// One copy for every G.  Lane k (k < G) returns the parameters of component k; false = a class is empty
+// ("mixing proportion fell below threshold": the row has no valid model).
+// ---------------------------------------------------------------------------------------------
+template <int TW>
+__device__ __noinline__ bool em_start(int G, const double* xs, int n, int lane, double* red, double& mu_own,
+                                      double& sig_own, double& pro_own) {
+    typedef Team<TW> T;
+    const double rteps = 1.4901161193847656e-08;
+    const double dn = (double)n;
+    const int tid = T::tid(lane);
+    const int kown = lane < G ? lane : 0;
+    const bool owner = lane < G;
+    double br[GMAX];
+    const int nbr = qclass_breaks(xs, n, G, br);
+    double b0 = nbr > 0 ? br[0] : INFINITY, b1 = nbr > 1 ? br[1] : INFINITY;
+    double b2 = nbr > 2 ? br[2] : INFINITY, b3 = nbr > 3 ? br[3] : INFINITY;
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+    for (int i = tid; i < n; i += T::NT) {
+        double x = xs[i];
+        int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
+#pragma unroll
+        for (int k = 0; k < GMAX; k++) {
+            if (k == cl) { v[k] += 1.0; v[GMAX + k] += x; }
+        }
+    }
+    double t = T::reduce(v, lane, red);
+    double cnt = slot(t, kown), sx = slot(t, GMAX + kown);
+    if (__any_sync(FULLMASK, owner && cnt <= rteps)) return false;
+    mu_own = sx / cnt;
+    pro_own = cnt / dn;
+    double m0 = __shfl_sync(FULLMASK, mu_own, 0), m1 = __shfl_sync(FULLMASK, mu_own, 1);
+    double m2 = __shfl_sync(FULLMASK, mu_own, 2), m3 = __shfl_sync(FULLMASK, mu_own, 3);
+    double m4 = __shfl_sync(FULLMASK, mu_own, 4);
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.0;
+    for (int i = tid; i < n; i += T::NT) {
+        double x = xs[i];
+        int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
+        double m = cl == 0 ? m0 : cl == 1 ? m1 : cl == 2 ? m2 : cl == 3 ? m3 : m4;
+        double d = x - m;
+        double dd = d * d;
+#pragma unroll
+        for (int k = 0; k < GMAX; k++) {
+            if (k == cl) v[k] += dd;
+        }
+    }
+    t = T::reduce(v, lane, red);
+    sig_own = slot(t, kown) / cnt;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // G >= 2 row: qclass start, EM (mclust me1v semantics: M-step first, stop when the relative change of
 // the log-likelihood is <= 1e-5), BIC, extra M-step, MAP label statistics.
-// One copy of this code serves every G: the scalar M-step runs once per warp with lane k owning
-// component k (lanes >= G shadow component 0), only the point loops are specialised on G.
+// One copy of this code serves every G: the scalar M-step runs once per warp with lane k owning component k
+// (lanes >= G shadow component 0), only the point loops are specialised on G.
 // ---------------------------------------------------------------------------------------------
 template <int TW, bool BUDGET>
 __device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, Row* row, WarpStats* st,
@@ -541,7 +678,6 @@ __device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, R
     typedef Team<TW> T;
     const double eps = DBL_EPSILON, rteps = 1.4901161193847656e-08, tol = 1e-5;
     const double dn = (double)n;
-    const int tid = T::tid(lane);
     const bool lead0 = T::lead() && lane == 0;
     if (lead0) { row->valid = 0; row->iters = 0; }
     if (G > n) return false;   // mclustBIC: G <- G[G <= n]
@@ -549,49 +685,8 @@ __device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, R
     const bool owner = lane < G;
     const double range2 = (xs[n - 1] - xs[0]) * (xs[n - 1] - xs[0]);   // xs is sorted: every |x - mu_k| <= range
 
-    double br[GMAX];
-    const int nbr = qclass_breaks(xs, n, G, br);
-    double b0 = nbr > 0 ? br[0] : INFINITY, b1 = nbr > 1 ? br[1] : INFINITY;
-    double b2 = nbr > 2 ? br[2] : INFINITY, b3 = nbr > 3 ? br[3] : INFINITY;
-
-    // ---- first M-step from the hard quantile classes (z = unmap(qclass)) ----
     double mu_own, sig_own, pro_own;
-    {
-        double v[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = 0.0;
-        for (int i = tid; i < n; i += T::NT) {
-            double x = xs[i];
-            int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
-#pragma unroll
-            for (int k = 0; k < GMAX; k++) {
-                if (k == cl) { v[k] += 1.0; v[GMAX + k] += x; }
-            }
-        }
-        double t = T::reduce(v, lane, red);
-        double cnt = slot(t, kown), sx = slot(t, GMAX + kown);
-        if (__any_sync(FULLMASK, owner && cnt <= rteps)) return false;   // an empty class: "mixing proportion fell below threshold"
-        mu_own = sx / cnt;
-        pro_own = cnt / dn;
-        double m0 = __shfl_sync(FULLMASK, mu_own, 0), m1 = __shfl_sync(FULLMASK, mu_own, 1);
-        double m2 = __shfl_sync(FULLMASK, mu_own, 2), m3 = __shfl_sync(FULLMASK, mu_own, 3);
-        double m4 = __shfl_sync(FULLMASK, mu_own, 4);
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = 0.0;
-        for (int i = tid; i < n; i += T::NT) {
-            double x = xs[i];
-            int cl = (x >= b0) + (x >= b1) + (x >= b2) + (x >= b3);
-            double m = cl == 0 ? m0 : cl == 1 ? m1 : cl == 2 ? m2 : cl == 3 ? m3 : m4;
-            double d = x - m;
-            double dd = d * d;
-#pragma unroll
-            for (int k = 0; k < GMAX; k++) {
-                if (k == cl) v[k] += dd;
-            }
-        }
-        t = T::reduce(v, lane, red);
-        sig_own = slot(t, kown) / cnt;
-    }
+    if (!em_start<TW>(G, xs, n, lane, red, mu_own, sig_own, pro_own)) return false;
 
     double hold = 8.988465674311579e307, hood = 0.0;   // "previous" log-likelihood sentinel (FLMAX/2 in mclust)
     int iter = 0;
@@ -603,7 +698,7 @@ __device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, R
         // E-step constants of the owned component: nh = -1/(2 sigsq), lc = log(pro) - (log 2pi + log sigsq)/2
         const double rsig = fast_rcp(sig_own);
         nh_own = -0.5 * rsig;
-        lc_own = 0.5 * log(pro_own * pro_own * rsig) - 0.5 * PI2LOG;
+        lc_own = 0.5 * fast_log(pro_own * pro_own * rsig) - 0.5 * PI2LOG;
         iter++;
         T::sync();
         if (owner && T::lead()) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }

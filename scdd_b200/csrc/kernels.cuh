@@ -441,11 +441,13 @@ constexpr int FIT_MAX_WARPS = SCDD_FIT_WARPS;
 
 // uploads the 2^(j/2^TB) table to the current device (once per device per process)
 inline cudaError_t init_exp_table() {
-    return cudaMemcpyToSymbol(EXP_TABLE_GLOBAL, exp_table_host(), SCDD_EXP_TABLE_SIZE * sizeof(double));
+    cudaError_t e = cudaMemcpyToSymbol(EXP_TABLE_GLOBAL, exp_table_host(), SCDD_EXP_TABLE_SIZE * sizeof(double));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(LOG_TABLE_GLOBAL, log_table_host(), SCDD_LOG_TABLE_SIZE * sizeof(LogTab));
 }
 constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
 constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
-constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8;   // the CTA's 2^(j/2048) table (16 KB of static shared memory)    // larger fit-sets are run by a whole CTA
+constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8 + SCDD_LOG_TABLE_SIZE * 16;   // the CTA's 2^(j/2048) table (16 KB of static shared memory)    // larger fit-sets are run by a whole CTA
 
 // per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
@@ -466,6 +468,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tid = T::tid(lane);
     for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) EXP_TABLE_SH[i] = EXP_TABLE_GLOBAL[i];   // 2^(j/2048)
+    for (int i = threadIdx.x; i < SCDD_LOG_TABLE_SIZE; i += blockDim.x) LOG_TABLE_SH[i] = LOG_TABLE_GLOBAL[i];
     __syncthreads();
     unsigned char* region = smem_raw + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned

@@ -426,7 +426,8 @@ struct Pipeline {
             const int v = std::atoi(e);
             if ((v == 4 || v == 8 || v == 32) && fits(v, 1)) return v;
         }
-        for (int gs : {4, 8})
+        // measured on B200 (profiles/permgen_groups_r02.txt): 8 lanes per gene is the fastest of the three where it fits
+        for (int gs : {8})
             if (fits(gs, 4)) return gs;
         return 32;
     }
@@ -1480,17 +1481,34 @@ int32_t scdd_selftest_exp(const double* x, int32_t n, double* out) {
     return SCDD_OK;
 }
 
-// softmax of G log-terms exactly as the E-step computes it (integer shift, table exp, Newton reciprocal)
-int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* logsumexp) {
+// softmax of G log-terms exactly as the E-step computes it (integer shift, table exp, Newton reciprocal; a point whose
+// every term is saturated is redone on a_k - max a_k, as the kernel's saturating pass does)
+int32_t scdd_selftest_softmax(const double* a_in, int32_t G, double* z, double* logsumexp) {
     if (G < 1 || G > SCDD_GMAX) return fail(SCDD_ERR_BAD_ARG, "G out of range");
     const double* tab = exp_table_host();
-    double t[SCDD_GMAX], s[SCDD_GMAX], e[SCDD_GMAX];
+    double a[SCDD_GMAX], t[SCDD_GMAX], s[SCDD_GMAX], e[SCDD_GMAX];
     int nn[SCDD_GMAX], M = 0;
-    for (int k = 0; k < G; k++) { t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]); M = (k == 0 || nn[k] > M) ? nn[k] : M; }
+    double far = 0.0;
+    for (int k = 0; k < G; k++) a[k] = a_in[k];
+    for (int pass = 0; pass < 2; pass++) {
+        for (int k = 0; k < G; k++) { t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]); M = (k == 0 || nn[k] > M) ? nn[k] : M; }
+        if (M != expc::NSAT || pass == 1) break;
+        far = a[0];
+        for (int k = 1; k < G; k++) far = std::fmax(far, a[k]);
+        for (int k = 0; k < G; k++) a[k] -= far;
+    }
     double S = 0.0;
     for (int k = 0; k < G; k++) { s[k] = term_s(term_r(a[k], t[k])); e[k] = term_e(s[k], nn[k], M, tab); S += e[k]; }
     for (int k = 0; k < G; k++) z[k] = e[k] / S;
-    if (logsumexp) *logsumexp = std::log(S) + (double)M * expc::LN2_T;
+    if (logsumexp) *logsumexp = fast_log_tab(S, log_table_host()) + (double)M * expc::LN2_T + far;
+    return SCDD_OK;
+}
+
+// the kernels' table-driven logarithm (host build of the same source): out[i] = log(x[i]) for positive normal x
+int32_t scdd_selftest_log(const double* x, int32_t n, double* out) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    const LogTab* tab = log_table_host();
+    for (int i = 0; i < n; i++) out[i] = fast_log_tab(x[i], tab);
     return SCDD_OK;
 }
 

@@ -115,6 +115,44 @@ def test_kernel_softmax_matches_high_precision():
     assert worst_z < 2e-14 and worst_l < 1e-15
 
 
+def test_kernel_softmax_when_every_term_is_saturated():
+    """log-terms below -2^18 saturate; a point that far from ALL components must still give the weight to the
+    nearest one (mclust's exp(t_k - max t) does), not share it among the saturated terms"""
+    L = _lib.lib()
+    for a, want in (([-4.5e5, -2.5e6], [1.0, 0.0]), ([-2.5e6, -4.5e5, -9e5], [0.0, 1.0, 0.0]),
+                    ([-3.0e5 - 0.5, -3.0e5], [1.0 / (1.0 + np.exp(0.5)), 1.0 / (1.0 + np.exp(-0.5))]),
+                    ([-2.0e5, -4.5e5], [1.0, 0.0])):                  # one finite, one saturated
+        a = np.array(a)
+        z = np.zeros(a.size)
+        lse = np.zeros(1)
+        assert L.scdd_selftest_softmax(a.ctypes.data, a.size, z.ctypes.data, lse.ctypes.data) == 0
+        np.testing.assert_allclose(z, want, rtol=1e-12, atol=1e-300)
+        al = a.astype(np.longdouble)
+        ref = float(np.log(np.exp(al - al.max()).sum()) + al.max())
+        assert abs(lse[0] - ref) <= 1e-15 * abs(ref)
+
+
+def test_kernel_log_accuracy():
+    """the EM loop's table-driven logarithm (host build of the same source) against long-double log"""
+    rng = np.random.default_rng(4)
+    L = _lib.lib()
+    x = np.concatenate([np.exp(rng.uniform(-50, 50, 200000)),            # M-step arguments pro^2 / sigsq
+                        1.0 + rng.random(50000) * 4.0 ** rng.integers(0, 256, 50000).clip(0, 200),   # running products
+                        [1.0, 0.5, 2.0, 4e-4, 5.0 ** 256, 1.0 + 2.0 ** -52, 1.0 - 2.0 ** -53, 2.2250738585072014e-308,
+                         1.7976931348623157e308]])
+    x = np.ascontiguousarray(x[np.isfinite(x) & (x > 0)])
+    out = np.zeros_like(x)
+    assert L.scdd_selftest_log(x.ctypes.data, x.size, out.ctypes.data) == 0
+    ref = np.log(x.astype(np.longdouble))
+    err = np.abs(out.astype(np.longdouble) - ref)
+    # what the EM loop needs is ABSOLUTE accuracy (the logs are summed into a log-likelihood of magnitude >= 1):
+    # within 1.5 ulp of the result where |log x| > 1, within 2e-16 absolute below (no special case near x = 1)
+    big = np.abs(ref) > 1
+    assert float((err[big] / np.spacing(np.abs(ref[big].astype(np.float64)))).max()) < 1.5
+    assert float(err[~big].max()) < 2e-16
+    assert abs(out[np.nonzero(x == 1.0)[0][0]]) < 2e-17
+
+
 def test_r_rng_host_matches_oracle_and_known_answers():
     # R >= 3.6: set.seed(1); sample(1:10)  /  set.seed(42); sample(1:10)
     assert hp.mt_sample_perms(1, 10, 1)[0].tolist() == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
