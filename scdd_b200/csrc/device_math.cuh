@@ -17,13 +17,16 @@ namespace scdd {
 // The E-step's softmax terms.  For the log-terms t_k of one point (k = 1..G) the kernels need
 // e_k = exp(t_k - shift) for ANY common shift that keeps the sum in range (log-sum-exp is shift invariant).
 //   N_k = rint(t_k * 2^TB/ln2)  (TB = 11)                 (magic-number rounding; also the exp range reduction)
-//   M   = max_k N_k                          (integer max: the shift is M ln2/2^TB, the max rounded to the grid)
-//   r_k = t_k - N_k * c,  c = fl(ln2/2^TB)   (ONE fma: the error N_k (ln2/2^TB - c) splits into M (..), common to all k
-//                                             and cancelled exactly when the log-likelihood adds the shift back as
-//                                             M * c with the same c, and (N_k - M)(..) <= 1e-16 for every term that matters)
-//   e_k = 2^((N_k - M)/2^TB) exp(r_k) = 2^(D >> TB) * T[D & (2^TB - 1)] * (1 + s(r_k)),  D = N_k - M <= 0
+//   H_k = N_k >> TB,  j_k = N_k & (2^TB - 1)              (whole powers of two / table index: N_k = 2^TB H_k + j_k)
+//   Mh  = max_k H_k                          (integer max: the shift is Mh ln2, the max rounded DOWN to a whole power of 2)
+//   r_k = t_k - N_k * c,  c = fl(ln2/2^TB)   (ONE fma: the error N_k (ln2/2^TB - c) splits into 2^TB Mh (..), common to
+//                                             all k and cancelled exactly when the log-likelihood adds the shift back as
+//                                             Mh * 2^TB c with the same c, and a remainder <= 1e-16 for every term that matters)
+//   e_k = 2^(H_k - Mh) * T[j_k] * (1 + s(r_k)),  the largest term lies in [1, 2), the sum in [1, 2G)
 // s(r) = exp(r) - 1 by a degree-3 polynomial on |r| <= ln2/4096 (truncation 3.4e-17), T = 2048-entry table of
-// 2^(j/2048) (16 KB of shared memory per CTA).
+// 2^(j/2048) (16 KB of shared memory per CTA).  Because the shift is a multiple of 2^TB the table index j_k does not
+// depend on the maximum: the lookup is issued as soon as N_k exists and its latency hides under the polynomial
+// (round 1 shifted by max N_k itself and stalled on the lookup at the end of the integer chain).
 // fp64 cost per term: 1 (t) + 1 (kf) + 1 (r) + 2 (polynomial) + 1 (s) + 1 (table fma) = 7; max, shift, table index
 // and 2^k scaling are integer instructions.  These helpers are the single source of the arithmetic: the kernels
 // issue them column-wise over the G (or 2G) terms of a point, the host self-test calls them term by term.
@@ -38,8 +41,10 @@ constexpr double L2E_T = 2954.639443740597;            // 2^TB / ln 2
 constexpr double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: rint() in the low mantissa bits
 constexpr double LN2_T = 0.00033845077175778578;       // fl(ln2 / 2^TB)
 constexpr double C2 = 0.5, C3 = 1.0 / 6.0;
-constexpr int NSAT = -(1 << 30);                       // N of a log-term below -2^19 ("minus infinity")
-constexpr int DMIN = -1021 * SCDD_EXP_TABLE_SIZE;      // smallest shift kept: 2^-1021 (the reference zeroes below e^-708)
+constexpr int NSAT = -(1 << 30);                       // N of a log-term below -2^18 ("minus infinity")
+constexpr int HSAT = NSAT >> SCDD_EXP_TABLE_BITS;      // its H = N >> TB
+constexpr int KMIN = -1021;                            // smallest power of two kept (the reference zeroes below e^-708)
+constexpr double LN2_STEP = 0.00033845077175778578 * SCDD_EXP_TABLE_SIZE;   // 2^TB * LN2_T, exact: the log of one unit of Mh
 }  // namespace expc
 
 // 2^(j / 2^TB), j = 0 .. 2^TB - 1, correctly rounded from long double (host; uploaded to the device once)
@@ -87,12 +92,13 @@ SCDD_HD double term_s(double r) {
     p = fma(p, r, 1.0);
     return p * r;
 }
-SCDD_HD double term_e(double s, int n, int M, const double* tab) {
-    int D = n - M;
-    if (D < expc::DMIN) D = expc::DMIN;
-    const double T = tab[D & expc::TMASK];
+SCDD_HD int term_h(int n) { return n >> expc::TB; }
+SCDD_HD double term_e(double s, int n, int Mh, const double* tab) {
+    int k = (n >> expc::TB) - Mh;
+    if (k < expc::KMIN) k = expc::KMIN;
+    const double T = tab[n & expc::TMASK];
     const double v = fma(T, s, T);
-    return from_words(hi_word(v) + ((D >> expc::TB) << 20), lo_word(v));
+    return from_words(hi_word(v) + (k << 20), lo_word(v));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -189,11 +189,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // G = 5, where the register file is the scarcer resource (load_params).
 // 2^((D mod 2048)/2048) from the CTA's table: mask, then one multiply-add forms the shared address
 // (the compiler's own sequence for tab[D & 2047] is shift, and, add).
-__device__ __forceinline__ double exp_table_sh(int D) {
+__device__ __forceinline__ double exp_table_sh(int N) {
     const unsigned base = (unsigned)__cvta_generic_to_shared(EXP_TABLE_SH);
     unsigned addr;
     double T;
-    asm("{ .reg .b32 j; and.b32 j, %1, %2; mad.lo.u32 %0, j, 8, %3; }" : "=r"(addr) : "r"(D), "n"(expc::TMASK), "r"(base));
+    asm("{ .reg .b32 j; and.b32 j, %1, %2; mad.lo.u32 %0, j, 8, %3; }" : "=r"(addr) : "r"(N), "n"(expc::TMASK), "r"(base));
     asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
     return T;
 }
@@ -261,8 +261,8 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
                                              double (&q)[U * G], double (&S)[U], int (&M)[U], double* far = nullptr) {
     using namespace expc;
     constexpr int N = U * G;
-    double a[N], t[N], r[N], p[N], h[G], l[G];
-    int n[N];
+    double a[N], t[N], r[N], p[N], h[G], l[G], T[N];
+    int n[N], nh[N];
 #pragma unroll
     for (int k = 0; k < G; k++) {
         double m;
@@ -282,12 +282,16 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
     for (int i = 0; i < N; i++) n[i] = SAT ? term_n(a[i], t[i]) : __double2loint(t[i]);
 #pragma unroll
-    for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&n[u * G]);
+    for (int i = 0; i < N; i++) T[i] = P::lookup(n[i]);          // 2^(j/2048), j = N & 2047: independent of the shift
+#pragma unroll
+    for (int i = 0; i < N; i++) nh[i] = n[i] >> TB;
+#pragma unroll
+    for (int u = 0; u < U; u++) M[u] = tree_imax<G>(&nh[u * G]);
     if (SAT) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             double amax = 0.0;
-            if (M[u] == NSAT) {            // cold: every term saturated
+            if (M[u] == HSAT) {            // cold: every term saturated
                 amax = a[u * G];
 #pragma unroll
                 for (int k = 1; k < G; k++) amax = fmax(amax, a[u * G + k]);
@@ -297,8 +301,10 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
                     a[i] = __dsub_rn(a[i], amax);
                     t[i] = fma(a[i], prm.c(0), MAGIC);
                     n[i] = term_n(a[i], t[i]);
+                    T[i] = P::lookup(n[i]);
+                    nh[i] = n[i] >> TB;
                 }
-                M[u] = tree_imax<G>(&n[u * G]);
+                M[u] = tree_imax<G>(&nh[u * G]);
             }
             if (far) far[u] = amax;
         }
@@ -322,11 +328,10 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
 #pragma unroll
         for (int k = 0; k < G; k++) {                                                      // term_e
             const int i = u * G + k;
-            const int D = max(n[i] - M[u], DMIN);
-            const double T = P::lookup(D);
-            const double v = fma(T, p[i], T);
-            int hi;   // hi(v) + ((D >> TB) << 20) as shift + multiply-add (two integer instructions, not three)
-            asm("{ .reg .s32 k; shr.s32 k, %1, %2; mad.lo.s32 %0, k, 1048576, %3; }" : "=r"(hi) : "r"(D), "n"(TB), "r"(__double2hiint(v)));
+            const double v = fma(T[i], p[i], T[i]);
+            int hi;   // hi(v) + (max(H - Mh, KMIN) << 20): add-max, then multiply-add (two integer instructions)
+            asm("{ .reg .s32 k; sub.s32 k, %1, %2; max.s32 k, k, %3; mad.lo.s32 %0, k, 1048576, %4; }"
+                : "=r"(hi) : "r"(nh[i]), "r"(M[u]), "n"(KMIN), "r"(__double2hiint(v)));
             e[i] = __hiloint2double(hi, __double2loint(v));
         }
     }
@@ -415,7 +420,7 @@ struct Team {
 template <int G, int U>
 __device__ __forceinline__ void accumulate_back(const double (&e)[U * G], const double (&d)[U * G], const double (&q)[U * G],
                                                 const double (&S)[U], const int (&M)[U], double (&A)[G], double (&B)[G],
-                                                double (&C)[G], double& pl, long long& hs) {
+                                                double (&C)[G], double& pl, int& hs) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
         double rs = rcp_sum(S[u]);
@@ -427,17 +432,13 @@ __device__ __forceinline__ void accumulate_back(const double (&e)[U * G], const 
             C[k] = fma(z, q[u * G + k], C[k]);
         }
         pl *= S[u];      // sum_i log S_i is taken as the log of a running product (S in (0.97, 1.03 G])
-#ifdef SCDD_HS32_EXPERIMENT
-        hs = (long long)((int)hs + M[u]);
-#else
-        hs += M[u];      // the shifts are integers: summed exactly, off the fp64 pipe
-#endif
+        hs += M[u];      // the shifts are whole powers of two, |Mh| <= 2^19: summed exactly in 32 bits over a 256-point chunk
     }
 }
 
 template <int G, int U, bool SAT, class P>
 __device__ __forceinline__ void accumulate_points(const double (&x)[U], const P& prm, double (&A)[G], double (&B)[G],
-                                                  double (&C)[G], double& pl, long long& hs, double& hfar) {
+                                                  double (&C)[G], double& pl, int& hs, double& hfar) {
     double e[U * G], d[U * G], q[U * G], S[U];
     int M[U];
     if (SAT) {
@@ -485,6 +486,9 @@ __device__ __forceinline__ auto load_params(const double* pm) {
 #ifndef SCDD_LOOP_UNROLL
 #define SCDD_LOOP_UNROLL 1
 #endif
+#ifndef SCDD_PREFETCH_X
+#define SCDD_PREFETCH_X 0
+#endif
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            double (&v)[16]) {
@@ -501,26 +505,47 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
     for (int base = 0; base < n; base += CHUNK) {
         const int stop = (n - base < CHUNK) ? n : base + CHUNK;
         double pl = 1.0;
+        int hc = 0;
         // pointer-bumped loops: the load is [register + immediate] and the bound test compares addresses
         const double* px = xs + base + Team<TW>::tid(lane);
         const double* const pend = xs + stop;
+        if (U == 1) {
+#if SCDD_PREFETCH_X
+            // the next point is loaded while the current one is processed (the load otherwise opens every iteration
+            // with a shared-memory round trip that nothing can overlap)
+            double xn = (px < pend) ? *px : 0.0;
+#pragma unroll 1
+            while (px < pend) {
+                double x[1] = {xn};
+                px += NT;
+                if (px < pend) xn = *px;
+                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+            }
+#else
 #pragma unroll LOOP_UNROLL
-        for (; px + NT * (U - 1) < pend; px += NT * U) {
-            double x[U];
+            for (; px < pend; px += NT) {
+                double x[1] = {*px};
+                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+            }
+#endif
+        } else {
+#pragma unroll 1
+            for (; px + NT * (U - 1) < pend; px += NT * U) {
+                double x[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) x[u] = px[NT * u];
-            accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hs, hfar);
-        }
-        if (U > 1) {
+                for (int u = 0; u < U; u++) x[u] = px[NT * u];
+                accumulate_points<G, U, SAT>(x, prm, A, B, C, pl, hc, hfar);
+            }
 #pragma unroll 1
             for (; px < pend; px += NT) {
                 double x[1] = {*px};
-                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hs, hfar);
+                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
             }
         }
+        hs += hc;
         hl += fast_log(pl);
     }
-    hl = fma((double)hs, expc::LN2_T, hl);   // log-likelihood: sum_i log S_i + c sum_i M_i, the SAME c as in term_r
+    hl = fma((double)hs, expc::LN2_STEP, hl);   // log-likelihood: sum_i log S_i + 2^TB c sum_i Mh_i, the SAME c as in term_r
     if (SAT) hl += hfar;
     // weight of the last component from sum_k z_k = 1: this thread's point count minus the other weights
     const int tid = Team<TW>::tid(lane);

@@ -1491,8 +1491,11 @@ int32_t scdd_selftest_softmax(const double* a_in, int32_t G, double* z, double* 
     double far = 0.0;
     for (int k = 0; k < G; k++) a[k] = a_in[k];
     for (int pass = 0; pass < 2; pass++) {
-        for (int k = 0; k < G; k++) { t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]); M = (k == 0 || nn[k] > M) ? nn[k] : M; }
-        if (M != expc::NSAT || pass == 1) break;
+        for (int k = 0; k < G; k++) {
+            t[k] = term_t(a[k]); nn[k] = term_n(a[k], t[k]);
+            M = (k == 0 || term_h(nn[k]) > M) ? term_h(nn[k]) : M;
+        }
+        if (M != expc::HSAT || pass == 1) break;
         far = a[0];
         for (int k = 1; k < G; k++) far = std::fmax(far, a[k]);
         for (int k = 0; k < G; k++) a[k] -= far;
@@ -1500,7 +1503,7 @@ int32_t scdd_selftest_softmax(const double* a_in, int32_t G, double* z, double* 
     double S = 0.0;
     for (int k = 0; k < G; k++) { s[k] = term_s(term_r(a[k], t[k])); e[k] = term_e(s[k], nn[k], M, tab); S += e[k]; }
     for (int k = 0; k < G; k++) z[k] = e[k] / S;
-    if (logsumexp) *logsumexp = fast_log_tab(S, log_table_host()) + (double)M * expc::LN2_T + far;
+    if (logsumexp) *logsumexp = fast_log_tab(S, log_table_host()) + (double)M * expc::LN2_STEP + far;
     return SCDD_OK;
 }
 
