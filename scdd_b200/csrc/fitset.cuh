@@ -198,28 +198,17 @@ __device__ __forceinline__ double exp_table_sh(int N) {
     return T;
 }
 
-#ifndef SCDD_PIN_CONST_MAXG
-#define SCDD_PIN_CONST_MAXG 0       // G up to which the three exp constants are held in registers across the point loop
-#endif
 template <int G, bool GTAB = false>
 struct ParamsReg {
     double mu[G], nh[G], lc[G];
-    double kc[3];   // exp constants (only live when pinned; otherwise every use reads the constant bank)
-    static constexpr bool PIN = !GTAB && G <= SCDD_PIN_CONST_MAXG;
-    __device__ __forceinline__ double c(int i) const { return PIN ? kc[i] : EXP_TAB_CONST[i]; }
-    __device__ __forceinline__ void pin() {
-        if (PIN) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) asm volatile("ld.const.f64 %0, [%1];" : "=d"(kc[i]) : "l"(&EXP_TAB_CONST[i]));
-        }
-    }
+    __device__ __forceinline__ static double c(int i) { return EXP_TAB_CONST[i]; }
     // 2^(j/2048): the CTA's shared copy, or (GTAB, label_of outside the fit loop) the global source
     __device__ __forceinline__ static double lookup(int D) { return GTAB ? EXP_TABLE_GLOBAL[D & expc::TMASK] : exp_table_sh(D); }
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const { m = mu[k]; h = nh[k]; l = lc[k]; }
 };
 struct ParamsSmem {
     __device__ __forceinline__ static double lookup(int D) { return exp_table_sh(D); }
-    __device__ __forceinline__ double c(int i) const { return EXP_TAB_CONST[i]; }
+    __device__ __forceinline__ static double c(int i) { return EXP_TAB_CONST[i]; }
     unsigned addr;   // shared-window address of the warp's {mu, nh, lc, pad}[GMAX] block (32 B per component)
     __device__ __forceinline__ void get(int k, double& m, double& h, double& l) const {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(h) : "r"(addr + 32u * k));
@@ -310,11 +299,7 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
         }
     }
 #pragma unroll
-#ifdef SCDD_I2F_EXPERIMENT
-    for (int i = 0; i < N; i++) p[i] = SAT ? __dsub_rn(t[i], MAGIC) : (double)n[i];        // same value, conversion pipe
-#else
     for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
-#endif
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = fma(p[i], prm.c(1), a[i]);
 #pragma unroll
@@ -472,7 +457,6 @@ __device__ __forceinline__ auto load_params(const double* pm) {
         ParamsReg<G> p;
 #pragma unroll
         for (int k = 0; k < G; k++) { p.mu[k] = pm[4 * k]; p.nh[k] = pm[4 * k + 1]; p.lc[k] = pm[4 * k + 2]; }
-        p.pin();
         return p;
     }
 #else
@@ -483,17 +467,10 @@ __device__ __forceinline__ auto load_params(const double* pm) {
 #endif
 }
 
-#ifndef SCDD_LOOP_UNROLL
-#define SCDD_LOOP_UNROLL 1
-#endif
-#ifndef SCDD_PREFETCH_X
-#define SCDD_PREFETCH_X 0
-#endif
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
                                            double (&v)[16]) {
     constexpr int NT = Team<TW>::NT;
-    constexpr int LOOP_UNROLL = SCDD_LOOP_UNROLL;
     const auto prm = load_params<G>(pm);
     double A[G], B[G], C[G];
 #pragma unroll
@@ -510,24 +487,23 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         const double* px = xs + base + Team<TW>::tid(lane);
         const double* const pend = xs + stop;
         if (U == 1) {
-#if SCDD_PREFETCH_X
-            // the next point is loaded while the current one is processed (the load otherwise opens every iteration
-            // with a shared-memory round trip that nothing can overlap)
-            double xn = (px < pend) ? *px : 0.0;
+            if (TW == 1) {
+                // a warp's slab is always shared memory: 32-bit shared-window addresses for the load and the bound test
+                unsigned sx = (unsigned)__cvta_generic_to_shared(px);
+                const unsigned send = (unsigned)__cvta_generic_to_shared(pend);
 #pragma unroll 1
-            while (px < pend) {
-                double x[1] = {xn};
-                px += NT;
-                if (px < pend) xn = *px;
-                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+                for (; sx < send; sx += NT * (unsigned)sizeof(double)) {
+                    double x[1];
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x[0]) : "r"(sx));
+                    accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+                }
+            } else {
+#pragma unroll 1
+                for (; px < pend; px += NT) {
+                    double x[1] = {*px};
+                    accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+                }
             }
-#else
-#pragma unroll LOOP_UNROLL
-            for (; px < pend; px += NT) {
-                double x[1] = {*px};
-                accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
-            }
-#endif
         } else {
 #pragma unroll 1
             for (; px + NT * (U - 1) < pend; px += NT * U) {
@@ -591,23 +567,20 @@ template <int G> struct Unroll { static constexpr int value = (G <= SCDD_UNROLL_
 
 // same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code, kept out of line
 // so that it does not weigh on the register allocation of the EM loop
-// returns the team total of slot (lane >> 1): the 16 partial sums never leave registers.
-// ONE non-inlined function holds the point loops of all four G: ptxas then allocates for the widest (G = 5, 128
-// registers, callee-saved registers spilled once in the prologue) and every loop keeps its 64-bit accumulators in
-// aligned pairs.  One function per G (tried in round 2) is allocated tightly enough to avoid the prologue spill, and
-// pays for it with ~20 register moves per point inside the loop.
-template <int TW>
-__device__ __noinline__ double estep_dispatch(int G, const double* xs, int n, int lane, const double* pm,
-                                              double* red) {
-    double v[16];
-    switch (G) {
-        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, v); break;
-        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, v); break;
-        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, v); break;
-        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, v); break;
-    }
-    return Team<TW>::reduce(v, lane, red);
-}
+// The EM loop's state, resident in the team's shared memory across the E-step call.  ptxas keeps
+// nothing in callee-saved registers around that call: in the round-1 shape every iteration reloaded ~45 spilled
+// values from local memory in ~9 dependent clusters (ncu: the caller's loop was 4.8 % of the executed instructions
+// but 10.6 % of the warp time, 60 % of it long-scoreboard stalls).  With the state in shared memory the loop holds
+// two registers across the call (context pointer, lane) and reads what it needs in one batch.
+struct EmCtx {
+    const double* xs;
+    double* pm;
+    double* red;
+    int n, G, iter, flags;          // flags bit 0: a stop test came within 1e-7 of the tolerance
+    double hold, range2, inv_n;
+    double sig[GMAX], pro[GMAX];    // mu lives in pm[4 k]
+};
+static_assert(sizeof(EmCtx) % 16 == 0, "keeps the slab 16-byte aligned");
 
 // same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code
 template <int TW>
@@ -621,6 +594,34 @@ __device__ __noinline__ double estep_dispatch_sat(int G, const double* xs, int n
         default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, v); break;
     }
     return Team<TW>::reduce(v, lane, red);
+}
+
+// returns the team total of slot (lane >> 1): the 16 partial sums never leave registers.
+// ONE non-inlined function holds the point loops of all four G: ptxas then allocates for the widest (G = 5, 128
+// registers, callee-saved registers spilled once in the prologue) and every loop keeps its 64-bit accumulators in
+// aligned pairs.  One function per G (tried in round 2) is allocated tightly enough to avoid the prologue spill, and
+// pays for it with ~20 register moves per point inside the loop.
+// Arguments come from the team's context (EmCtx).
+template <int TW>
+__device__ __noinline__ double estep_ctx(const EmCtx* cx, int lane) {
+    const int G = cx->G, n = cx->n;
+    const double* xs = cx->xs;
+    const double* pm = cx->pm;
+    // pointers that went through memory have lost their address space: say it again (LDS instead of generic loads)
+    __builtin_assume(__isShared(pm));
+    if (TW == 1) __builtin_assume(__isShared(xs));
+    double v[16];
+    switch (G) {
+        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, v); break;
+        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, v); break;
+        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, v); break;
+        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, v); break;
+    }
+    return Team<TW>::reduce(v, lane, cx->red);
+}
+template <int TW>
+__device__ __noinline__ double estep_ctx_sat(const EmCtx* cx, int lane) {
+    return estep_dispatch_sat<TW>(cx->G, cx->xs, cx->n, lane, cx->pm, cx->red);
 }
 
 template <int TW>
@@ -718,37 +719,59 @@ __device__ __noinline__ bool fit_row(int G, const double* xs, int n, int lane, R
     double A = 0.0, B = 0.0, C = 0.0, nh_own = 0.0, lc_own = 0.0;
     const double inv_n = 1.0 / dn;
     bool failed = false, near_tol = false, capped = false;
+    EmCtx* const cx = reinterpret_cast<EmCtx*>(pm + 4 * GMAX);
+    T::sync();
+    if (lead0) {
+        cx->xs = xs; cx->pm = pm; cx->red = red; cx->n = n; cx->G = G; cx->iter = 0; cx->flags = 0;
+        cx->hold = hold; cx->range2 = range2; cx->inv_n = inv_n;
+    }
+    if (owner && T::lead()) { pm[4 * lane] = mu_own; cx->sig[lane] = sig_own; cx->pro[lane] = pro_own; }
+    T::sync();
     for (;;) {
+        // ---- state of the owned component from shared memory, E-step constants ----
+        mu_own = cx->pm[4 * kown]; sig_own = cx->sig[kown]; pro_own = cx->pro[kown];
         if (__any_sync(FULLMASK, owner && sig_own <= eps)) { failed = true; break; }   // "sigma-squared falls below threshold"
-        // E-step constants of the owned component: nh = -1/(2 sigsq), lc = log(pro) - (log 2pi + log sigsq)/2
         const double rsig = fast_rcp(sig_own);
         nh_own = -0.5 * rsig;
         lc_own = 0.5 * fast_log(pro_own * pro_own * rsig) - 0.5 * PI2LOG;
-        iter++;
-        T::sync();
-        if (owner && T::lead()) { pm[4 * lane] = mu_own; pm[4 * lane + 1] = nh_own; pm[4 * lane + 2] = lc_own; }
+        if (owner && T::lead()) { cx->pm[4 * lane + 1] = nh_own; cx->pm[4 * lane + 2] = lc_own; }
         T::sync();
         // |t_k| <= |lc_k| + range^2 / (2 sigsq_k) with |lc_k| < 100: below 2^19 for every point iff the smallest
         // variance exceeds range^2 / 2^20; then the integer extraction needs no saturation test (fast pass)
-        const bool wide = !__any_sync(FULLMASK, owner && !(sig_own * 1.0e6 > range2));
-        const double t = wide ? estep_dispatch<TW>(G, xs, n, lane, pm, red)
-                              : estep_dispatch_sat<TW>(G, xs, n, lane, pm, red);
-        A = slot(t, kown); B = slot(t, G + kown); C = slot(t, 2 * G + kown);
-        hood = slot(t, 3 * G);
+        const bool wide = !__any_sync(FULLMASK, owner && !(sig_own * 1.0e6 > cx->range2));
+        const double t = wide ? estep_ctx<TW>(cx, lane) : estep_ctx_sat<TW>(cx, lane);
+        {
+            const int g = cx->G, k = lane < g ? lane : 0;
+            A = slot(t, k); B = slot(t, g + k); C = slot(t, 2 * g + k);
+            hood = slot(t, 3 * g);
+        }
+        hold = cx->hold;
+        iter = cx->iter + 1;
         // stop when |hold - hood| / (1 + |hood|) <= tol  (tested in product form: no division on the critical path)
         const double diff = fabs(hold - hood), bound = tol * (1.0 + fabs(hood));
-        hold = hood;
-        if (fabs(diff - bound) <= 1e-7 * bound) near_tol = true;
+        const bool close = fabs(diff - bound) <= 1e-7 * bound;
+        T::sync();                                  // every thread has read hold / iter
+        if (T::lead() && lane == 0) { cx->hold = hood; cx->iter = iter; if (close) cx->flags |= 1; }
         if (!(diff > bound)) break;
         if (iter >= (BUDGET ? iter_cap : EM_ITER_CAP)) { capped = true; break; }
         // ---- M-step (lane k: component k) ----
-        if (__any_sync(FULLMASK, owner && A <= rteps)) { failed = true; break; }
+        const bool own = lane < cx->G;
+        if (__any_sync(FULLMASK, own && A <= rteps)) { failed = true; break; }
         const double ra = fast_rcp(A);
         const double dm = B * ra;
-        mu_own = mu_own + dm;
-        sig_own = fma(-dm, dm, C * ra);
-        pro_own = A * inv_n;
+        if (own && T::lead()) {
+            cx->pm[4 * lane] = cx->pm[4 * lane] + dm;
+            cx->sig[lane] = fma(-dm, dm, C * ra);
+            cx->pro[lane] = A * cx->inv_n;
+        }
+        T::sync();
     }
+    T::sync();
+    // the loop's registers are gone by now: the state that the epilogue needs comes back from shared memory
+    mu_own = pm[4 * kown]; sig_own = cx->sig[kown]; pro_own = cx->pro[kown];
+    nh_own = pm[4 * kown + 1]; lc_own = pm[4 * kown + 2];
+    iter = cx->iter;
+    near_tol = (cx->flags & 1) != 0;
     // stopped by the caller's iteration budget (not by the safety cap): nothing is recorded, the caller re-runs the
     // whole fit-set elsewhere (fit_kernel, "deferred" items)
     if (BUDGET && capped && iter_cap < EM_ITER_CAP) return true;

@@ -449,10 +449,11 @@ constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fi
 constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
 constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8 + SCDD_LOG_TABLE_SIZE * 16;   // the CTA's 2^(j/2048) table (16 KB of static shared memory)    // larger fit-sets are run by a whole CTA
 
-// per-team shared-memory region: {mu, nh, lc, pad} x GMAX | Row[GMAX] | WarpStats | cross-warp reduction
+// per-team shared-memory region: {mu, nh, lc, pad} x GMAX | EmCtx | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
 __host__ __device__ constexpr size_t fit_region_head(int tw) {
-    return 4 * GMAX * sizeof(double) + GMAX * sizeof(Row) + sizeof(WarpStats) + (tw > 1 ? (size_t)tw * 16 * sizeof(double) : 0);
+    return 4 * GMAX * sizeof(double) + sizeof(EmCtx) + GMAX * sizeof(Row) + sizeof(WarpStats) +
+           (tw > 1 ? (size_t)tw * 16 * sizeof(double) : 0);
 }
 __host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
     return fit_region_head(1) + (size_t)np * sizeof(double);
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     __syncthreads();
     unsigned char* region = smem_raw + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
-    Row* rows = reinterpret_cast<Row*>(pm + 4 * GMAX);
+    Row* rows = reinterpret_cast<Row*>(reinterpret_cast<unsigned char*>(pm + 4 * GMAX) + sizeof(EmCtx));   // EmCtx sits between them
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
     double* red = reinterpret_cast<double*>(st + 1);
     double* xs = (TW > 1 && a.xs_global) ? a.xs_global + (size_t)blockIdx.x * a.np_max
