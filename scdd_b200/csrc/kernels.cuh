@@ -287,11 +287,11 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
                     if (n <= 32768u) {
                         // ceil(log2 m) <= 15: one 16-bit chunk per attempt, everything fits 32-bit arithmetic
                         uint32_t mask = (1u << bits) - 1u;
-                        while (i < n && used < PG_BLOCK) {
-                            const uint32_t v = (uint32_t)cand[used++] & mask;
+                        // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the active range
+                        // receives y[i]: the array ends up holding the permutation reversed.
+                        auto take = [&](uint32_t c16) {
+                            const uint32_t v = c16 & mask;
                             if (v < m) {
-                                // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the
-                                // active range receives y[i]: the array ends up holding the permutation reversed.
                                 const IdxT pick = arr[v];
                                 --m;
                                 arr[v] = arr[m];
@@ -302,7 +302,16 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
                                     mask = (1u << bits) - 1u;
                                 }
                             }
+                        };
+                        // four candidates per shared-memory load while a whole aligned quad is available: the loop is
+                        // latency-bound (few genes per SM fit shared memory), and the candidate load is half of the
+                        // dependent chain of a step
+                        while (i + 4 <= n && (used & 3) == 0 && used + 4 <= PG_BLOCK) {
+                            const uint2 q = *reinterpret_cast<const uint2*>(cand + used);
+                            used += 4;
+                            take(q.x & 0xffffu); take(q.x >> 16); take(q.y & 0xffffu); take(q.y >> 16);
                         }
+                        while (i < n && used < PG_BLOCK) take((uint32_t)cand[used++]);
                     } else {
                         const uint64_t one = 1;
                         uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);

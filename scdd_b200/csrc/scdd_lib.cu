@@ -439,7 +439,9 @@ struct Pipeline {
         const size_t cap = 200 * 1024;
         const size_t per_warp = permgen_smem_per_group(max_n, (int)sizeof(IdxT), GS) * (32 / GS);
         const int gpw = 32 / GS;
-        int wpb = (int)std::max<size_t>(1, std::min<size_t>(4, cap / per_warp));
+        size_t wpb_max = 4;
+        if (const char* e = std::getenv("SCDD_PERMGEN_WPB")) wpb_max = (size_t)std::max(1, std::atoi(e));   // A/B switch
+        int wpb = (int)std::max<size_t>(1, std::min<size_t>(wpb_max, cap / per_warp));
         wpb = std::max(1, std::min(wpb, (ngenes + gpw - 1) / gpw));
         const size_t smem = per_warp * wpb;
         const int blocks_needed = (ngenes + gpw * wpb - 1) / (gpw * wpb);
