@@ -188,6 +188,12 @@ int32_t scdd_dense_scan(const double* X, int64_t ngenes, int64_t ncells, int32_t
 int32_t scdd_dense_to_csr(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
                           const int32_t* genes, int32_t nsel, int32_t take_log, int32_t incl_zero,
                           const int64_t* gene_off, double* vals, int32_t* cond01);
+/* scdd_dense_cell_covariate: a per-cell covariate -- the cellular detection rate C of R/scDD.R:457 -- spread over the
+ * nonzero cells of the selected genes in CSR order: `C[y>0]` of every gene (R/permutations.R:216, R/classify.dd.R:341),
+ * i.e. the `cdr` argument of scdd_perm_bf / scdd_fedp.  gene_off as for scdd_dense_to_csr (zeros dropped). */
+int32_t scdd_dense_cell_covariate(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major,
+                                  const double* cell_values, const int32_t* genes, int32_t nsel, const int64_t* gene_off,
+                                  double* out);
 /* scdd_labels_to_dense: the Zhat matrices, R/scDD.R:528-552.  Z (same layout as X) = 0 where X == 0, the class
  * label on the nonzero cells of the selected genes (labels in CSR order over ALL their nonzero cells), 1 elsewhere.
  * which = -1: all cells (Zhat.combined); 0 / 1: only that condition's cells (Zhat.c1 / Zhat.c2 -- Z then has

@@ -66,7 +66,7 @@ EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set
            "scdd_fit_observed", "scdd_perm_bf", "scdd_perm_bf_ex", "scdd_release_cache", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
            "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax", "scdd_selftest_log",
-           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
+           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_dense_cell_covariate", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
 
 
 def lib_path():
@@ -115,6 +115,7 @@ def lib():
     i64 = C.c_int64
     L.scdd_dense_scan.argtypes = [vp, i64, i64, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.scdd_dense_to_csr.argtypes = [vp, i64, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
+    L.scdd_dense_cell_covariate.argtypes = [vp, i64, i64, C.c_int32, vp, vp, C.c_int32, vp, vp]
     L.scdd_labels_to_dense.argtypes = [vp, i64, i64, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp, vp]
     L.scdd_cluster_counts.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.scdd_fedp.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(Stats)]

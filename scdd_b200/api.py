@@ -193,9 +193,9 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         comps_c2 = hp.cluster_counts(cls_c, c01, off, min_size=min_size, which=1).astype(np.float64)
     cdr = None
     if adjust_perms:
-        Xf = X if sel is None else X[tofit]
-        C = (Xf > 0).sum(axis=0) / float(nf)                           # R/scDD.R:457, R/classify.dd.R:331
-        cdr = np.broadcast_to(C, Xf.shape)[Xf > 0]
+        # per-cell detection rate over the fitted genes (R/scDD.R:457, R/classify.dd.R:331), spread over the nonzero cells
+        C = ((X if sel is None else X[tofit]) > 0).sum(axis=0) / float(nf)
+        cdr = hp.cell_covariate(X, C, off, genes=sel)
     if permutations == 0:
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")

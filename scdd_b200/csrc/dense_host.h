@@ -138,6 +138,14 @@ inline bool to_csr(const View& v, const int32_t* cc, const int32_t* genes, int64
     return walk_selected(v, genes, nsel, gene_off, [](double x) { return x > 0; }, emit);
 }
 
+// a per-cell covariate (the cellular detection rate C of R/scDD.R:457) spread over the nonzero cells of the selected
+// genes in CSR order: what `C[y>0]` is for every gene (R/permutations.R:216, R/classify.dd.R:341)
+inline bool cell_values_to_csr(const View& v, const double* cell_values, const int32_t* genes, int64_t nsel,
+                               const int64_t* gene_off, double* out) {
+    return walk_selected(v, genes, nsel, gene_off, [](double x) { return x > 0; },
+                         [&](int64_t, int64_t c, double, int64_t p) { out[p] = cell_values[c]; });
+}
+
 // R/scDD.R:528-552: Z = 1, Z[X == 0] = 0, then the class labels of the fitted genes on their nonzero cells.
 // which = -1: all cells (Zhat.combined); 0 / 1: only the cells of that condition (Zhat.c1 / Zhat.c2), Z then has
 // that many columns.  labels are in CSR order over ALL nonzero cells of the selected genes.

@@ -1372,6 +1372,18 @@ int32_t scdd_dense_to_csr(const double* X, int64_t ngenes, int64_t ncells, int32
     return SCDD_OK;
 }
 
+int32_t scdd_dense_cell_covariate(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major,
+                                  const double* cell_values, const int32_t* genes, int32_t nsel, const int64_t* gene_off,
+                                  double* out) {
+    if (ngenes < 0 || ncells < 0 || nsel < 0 || !gene_off || ((!X || !cell_values) && ngenes * ncells > 0) ||
+        (gene_off[nsel] > 0 && !out))
+        return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    dense::View v{X, ngenes, ncells, col_major != 0};
+    if (!dense::cell_values_to_csr(v, cell_values, genes, nsel, gene_off, out))
+        return fail(SCDD_ERR_BAD_ARG, "gene_off does not match the nonzero cells of the selected genes");
+    return SCDD_OK;
+}
+
 int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,
                              int32_t which, const int32_t* genes, int32_t nsel, const int64_t* gene_off,
                              const int32_t* labels, double* Z) {

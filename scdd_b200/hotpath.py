@@ -73,6 +73,25 @@ def gene_csr(normcounts, condition, ref=None, log=True, incl_zero=False, genes=N
     return vals, cond01, gene_off
 
 
+def cell_covariate(normcounts, cell_values, gene_off, genes=None):
+    """A per-cell covariate (the detection rate C of R/scDD.R:457) on the nonzero cells of the selected genes, in CSR
+    order: the `cdr` argument of perm_bf / fedp (`C[y>0]` per gene, R/permutations.R:216)."""
+    X = np.asarray(normcounts, dtype=np.float64)
+    col_major = X.flags.f_contiguous and not X.flags.c_contiguous
+    if not col_major:
+        X = np.ascontiguousarray(X)
+    ng, nc = X.shape
+    cv = np.ascontiguousarray(cell_values, dtype=np.float64)
+    assert cv.size == nc
+    if genes is not None:
+        genes = np.ascontiguousarray(genes, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    out = np.empty(int(gene_off[-1]), dtype=np.float64)
+    _lib.check(_lib.lib().scdd_dense_cell_covariate(X.ctypes.data, ng, nc, int(col_major), cv.ctypes.data, _lib.ptr(genes),
+                                                    gene_off.size - 1, gene_off.ctypes.data, out.ctypes.data))
+    return out
+
+
 def labels_to_dense(normcounts, condition, labels, gene_off, genes=None, which=-1, ref=None):
     """Zhat matrix (R/scDD.R:528-552): 0 where the count is zero, the class label on the nonzero cells of the fitted
     genes, 1 elsewhere.  which = 0 / 1 keeps only that condition's columns."""
