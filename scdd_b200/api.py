@@ -11,11 +11,13 @@ names, argument meaning, error strings and result columns as the R functions it 
 All numerical work of the hot path happens in libscdd_b200.so (CUDA); this module contains no fitting code.
     feDP()      R/classify.dd.R:314-383  (the follow-up test of the non-significant genes)
 
-What stays in R in a real deployment and is therefore NOT reproduced here (out of scope /
-"next"): classifyDD (DE/DP/DM/DB labels of individual genes; Monte-Carlo with R's rt) and testZeroes
-(arm::bayesglm).  `DDcategory` is therefore "NS" / "DP" for the genes feDP settles, and None (NA) for the genes
-the reference hands to classifyDD (the significant ones and feDP's "NC" candidates); the R shim in r/ keeps
-calling the reference's own classifyDD on the lists this path produces.
+    classifyDD() R/classify.dd.R:86-238  (SURVEY 8f row 3: the DE / DP / DM / DB / NC pattern of the significant genes;
+                                      its Monte-Carlo test uses numpy's Student-t draws, not R's stream -- same
+                                      distribution, borderline genes may differ as between two R seeds)
+
+What stays in R and is NOT reproduced here: testZeroes (arm::bayesglm; SURVEY section 2, out of scope; the benchmark
+configs use testZeroes=FALSE).  With the R shim (r/R/scDD_b200.R) the reference's own classifyDD and testZeroes run
+on the lists this path produces.
 """
 import numpy as np
 
@@ -92,7 +94,8 @@ def testKS(dat, condition, inclZero=True, numDE=None, DEIndex=None, rownames=Non
     return out
 
 
-def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3, stats_out=None):
+def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3, stats_out=None,
+         precomputed=None):
     """R/classify.dd.R:314-383 over the CSR gene block (what `pe_mat[tofit, ]`, `condition` and the oa / c1 / c2
     class vectors are to the R function).  sig_genes: 0-based indices of the significant genes; cdr given means
     adjust.perms = TRUE.  Returns (ns_genes, pval_ns, cat): the BH-adjusted mean-shift p-values of the
@@ -105,7 +108,8 @@ def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr
     ns = np.nonzero(~sig)[0] if sig.any() else np.zeros(0, dtype=np.int64)
     if ns.size == 0:
         return ns, np.zeros(0), np.zeros(0, dtype=object)
-    p_shift, p_fisher, cnt, st = hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr, min_size=min_size)
+    p_shift, p_fisher, cnt, st = precomputed if precomputed is not None else \
+        hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr, min_size=min_size)
     if stats_out is not None:
         stats_out.update(st)
     pv = p_adjust_BH(p_shift[ns])
@@ -118,15 +122,101 @@ def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr
     return ns, pv, cat
 
 
+def _compress_labels(cls):
+    """R/classify.dd.R:124-158: when the label set has a gap (length(unique) != max) the labels above the FIRST missing
+    one move down by one (the reference handles one gap; so does this)."""
+    cls = np.asarray(cls).copy()
+    mx = int(cls.max())
+    present = np.unique(cls)
+    if present.size != mx:
+        missing = int(np.setdiff1d(np.arange(1, mx + 1), present)[0])
+        cls[cls > missing] -= 1
+    return cls
+
+
+def _posterior_params(y, cls, m0, s0, a0, b0):
+    """getPosteriorParams, R/classify.dd.R:19-37: per cluster k = 1..r the normal-gamma posterior (mk, sk, ak, bk)"""
+    r = np.unique(cls).size
+    nk = np.array([(cls == k).sum() for k in range(1, r + 1)], dtype=np.float64)
+    sy = np.array([y[cls == k].sum() for k in range(1, r + 1)])
+    syy = np.array([(y[cls == k] ** 2).sum() for k in range(1, r + 1)])
+    sk = s0 + nk
+    mk = (s0 * m0 + sy) / sk
+    ak = a0 + nk
+    bk = b0 + syy + s0 * m0 ** 2 - sk * mk ** 2
+    return mk, sk, ak, bk
+
+
+def _find_outliers(cls, min_size):
+    """findOutliers, R/Cluster_actions.R:78: labels of the clusters with at least min.size members"""
+    lab, cnt = np.unique(cls, return_counts=True)
+    return lab[cnt >= min_size].astype(int)
+
+
+def classifyDD(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, prior_param, adjust_perms=False, cdr=None, min_size=3,
+               rng=None, p_shift=None):
+    """classifyDD, R/classify.dd.R:86-238, over the CSR gene block: the DE / DP / DM / DB / NC pattern of each gene in
+    sig_genes (0-based) from the three clusterings.
+
+    The reference decides whether two cluster means differ by a Monte-Carlo draw: 10,000 Student-t variates per
+    cluster from R's own RNG stream (`rt`, :170-187), "different" iff all 10,000 sampled differences share a sign.  The
+    SAME test is made here with numpy's generator: the draws have the reference's distribution but not R's stream, so
+    a gene whose clusters sit right at the threshold can be labelled differently -- exactly as between two R runs with
+    different seeds.  (R's rt needs norm_rand / rgamma bit for bit, whose sources are not available offline; with the
+    R shim the reference's own classifyDD runs instead.)
+    p_shift: the unadjusted mean-shift p-values of scdd_fedp (Welch t / lm coefficient), used at :209-214."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    m0, s0, a0, b0 = prior_param["mu0"], prior_param["s0"], prior_param["a0"], prior_param["b0"]
+    out = []
+    for g in np.asarray(sig_genes, dtype=np.int64):
+        o, e = int(gene_off[g]), int(gene_off[g + 1])
+        y, c = logy[o:e], cond01[o:e]
+        oa = _compress_labels(cls_oa[o:e])
+        c1 = _compress_labels(cls_c[o:e][c == 0])
+        c2 = _compress_labels(cls_c[o:e][c == 1])
+        n_oa, n_c1, n_c2 = luOutlier(oa, min_size), luOutlier(c1, min_size), luOutlier(c2, min_size)
+        mk1, sk1, ak1, bk1 = _posterior_params(y[c == 0], c1, m0, s0, a0, b0)
+        mk2, sk2, ak2, bk2 = _posterior_params(y[c == 1], c2, m0, s0, a0, b0)
+        comparisons = []
+        for a in _find_outliers(c1, min_size):
+            for b in _find_outliers(c2, min_size):
+                d = (rng.standard_t(round(ak1[a - 1]), 10000) * np.sqrt(bk1[a - 1] / (ak1[a - 1] * sk1[a - 1])) + mk1[a - 1]
+                     - rng.standard_t(round(ak2[b - 1]), 10000) * np.sqrt(bk2[b - 1] / (ak2[b - 1] * sk2[b - 1])) - mk2[b - 1])
+                comparisons.append(1 if (d.min() > 0 or d.max() < 0) else 0)
+        tot = sum(comparisons)
+        if n_c1 == n_c2:
+            if n_c1 == 1:
+                cat = "DE" if tot > 0 else "NC"
+            elif n_oa == n_c1:
+                cat = "DP" if tot <= n_c1 else "NC"
+            elif n_oa > n_c1:
+                if tot > n_c1 * (n_c1 - 1):
+                    # multimodal DE: an overall mean shift as well (t.test / lm coefficient, :206-214)
+                    ps = p_shift[g] if p_shift is not None else hp.fedp(logy[o:e], c, np.array([0, e - o]), cls_oa[o:e],
+                                                                        cls_c[o:e], cdr=None if cdr is None else cdr[o:e],
+                                                                        min_size=min_size)[0][0]
+                    cat = "DE" if ps < 0.01 else "NC"
+                else:
+                    cat = "NC"
+            else:
+                cat = "NC"
+        else:
+            cat = "DB" if tot == len(comparisons) else "DM"
+        out.append(cat)
+    return np.array(out, dtype=object)
+
+
 def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=False, param=None,
          parallelBy=("Genes", "Permutations"), condition="condition", min_size=3, min_nonzero=None, level=0.05,
-         categorize=True, perm_source="device", verbose=True):
+         categorize=True, perm_source="device", verbose=True, classify=True):
     """R/scDD.R:217-602 with the per-gene work done on the GPU.
 
     param:       stands in for the BiocParallel param: dict(RNGseed=int[, devices=[...]]) -- RNGseed seeds the
                  per-gene L'Ecuyer-CMRG streams exactly as bplapply would.
     perm_source: "device" draws the permutations on the GPU (bit-exact R sampler); "host" draws them with the
                  library's host implementation of the same sampler and ships the indices (configs 1-2).
+    classify:    True runs classifyDD (DE / DP / DM / DB / NC labels; Monte-Carlo with numpy's generator -- see
+                 classifyDD); False leaves None for the genes the reference hands to classifyDD.
     """
     msg = (lambda s: print(s)) if verbose else (lambda s: None)
     if prior_param is None:
@@ -241,13 +331,28 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         # R/scDD.R:485-512: significant genes go to classifyDD (R; None here), the others start as "NS" and feDP
         # promotes some to "DP" or to classifyDD candidates ("NC" with adjusted p > level -> None here)
         cats = np.full(nf, "NS", dtype=object)
-        cats[sig] = None
+        # the unadjusted mean-shift p-values of every gene (one kernel): feDP needs them for the non-significant genes,
+        # classifyDD for its multimodal-DE rule
+        fe_all = hp.fedp(logy, c01, off, cls_oa, cls_c, cdr=cdr if adjust_perms else None, min_size=min_size) \
+            if nf else (np.zeros(0), np.zeros(0), np.zeros((0, 3), dtype=np.int32), {})
+        p_shift_all = fe_all[0]
+        crng = np.random.default_rng(int(param.get("classify_seed", param.get("RNGseed", 1))))
+        if classify:
+            cats[sig] = classifyDD(logy, c01, off, sig, cls_oa, cls_c, prior_param, adjust_perms=adjust_perms,
+                                   cdr=cdr if adjust_perms else None, min_size=min_size, rng=crng, p_shift=p_shift_all)
+        else:
+            cats[sig] = None
         ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=False, cdr=cdr if adjust_perms else None,
-                             min_size=min_size, stats_out=stats.setdefault("feDP", {}))
+                             min_size=min_size, stats_out=stats.setdefault("feDP", {}), precomputed=fe_all)
         cats[ns] = cat_ns
         with np.errstate(invalid="ignore"):
-            to_classify = (p_adjust_BH(pvals) > level) & (cats == "NC")
-        cats[to_classify] = None
+            to_classify = np.nonzero((p_adjust_BH(pvals) > level) & (cats == "NC"))[0]
+        if classify:
+            cats[to_classify] = classifyDD(logy, c01, off, to_classify, cls_oa, cls_c, prior_param,
+                                           adjust_perms=adjust_perms, cdr=cdr if adjust_perms else None,
+                                           min_size=min_size, rng=crng, p_shift=p_shift_all)
+        else:
+            cats[to_classify] = None
         for j, g in enumerate(tofit):
             cats_all[g] = cats[j]
     # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label

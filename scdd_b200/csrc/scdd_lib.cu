@@ -594,6 +594,8 @@ void scdd_default_cfg(scdd_cfg* c) {
     c->min_size = 3; c->restrict_ = 1; c->extra_mstep = 1; c->ks_old_pvalue = 0;
 }
 
+static void merge_stats(scdd_stats& dst, const scdd_stats& src);
+
 // ---------------------------------------------------------------- observed fits
 // EM iterations one warp spends on a single mixture before the fit-set is handed to a CTA (observed fits)
 static const int OBSERVED_ITER_BUDGET = 500;
@@ -671,9 +673,44 @@ int32_t scdd_fit_observed(const double* logy, const int64_t* gene_off, const int
     scdd_stats st;
     std::memset(&st, 0, sizeof(st));
     return guarded([&]() -> int {
-        // observed fits are 3 fit-sets per gene: one device is plenty; the first active device takes them
+        // 3 fit-sets per gene.  With several devices the genes are cut into contiguous ranges of equal cell counts (no
+        // gather: every range is a sub-block of the caller's arrays) and fitted concurrently, one host thread per device
         std::vector<int> devs = active_devices();
-        fit_observed_one(devs[0], logy, gene_off, cond01, ngenes, cfg, fits, cls_oa, cls_c, bf, den, &st);
+        if (devs.size() == 1 || ngenes < 64 * (int)devs.size()) {
+            fit_observed_one(devs[0], logy, gene_off, cond01, ngenes, cfg, fits, cls_oa, cls_c, bf, den, &st);
+        } else {
+            const size_t nd = devs.size();
+            std::vector<int> cut(nd + 1, ngenes);
+            cut[0] = 0;
+            const int64_t base = gene_off[0], total = gene_off[ngenes] - base;
+            for (size_t d = 1; d < nd; d++) {
+                const int64_t want = base + total * (int64_t)d / (int64_t)nd;
+                cut[d] = (int)(std::lower_bound(gene_off, gene_off + ngenes + 1, want) - gene_off);
+                cut[d] = std::max(cut[d], cut[d - 1]);
+            }
+            std::vector<scdd_stats> sts(nd);
+            std::vector<ScddError> errs(nd, ScddError{0, ""});
+            std::vector<std::thread> th;
+            for (size_t d = 0; d < nd; d++) {
+                th.emplace_back([&, d]() {
+                    std::memset(&sts[d], 0, sizeof(scdd_stats));
+                    const int g0 = cut[d], n = cut[d + 1] - cut[d];
+                    try {
+                        fit_observed_one(devs[d], logy, gene_off + g0, cond01, n, cfg, fits + 3 * (size_t)g0, cls_oa, cls_c,
+                                         bf ? bf + g0 : nullptr, den ? den + g0 : nullptr, &sts[d]);
+                    } catch (const ScddError& e) {
+                        errs[d] = e;
+                    } catch (const std::exception& e) {
+                        errs[d] = ScddError{SCDD_ERR_CUDA, e.what()};
+                    }
+                });
+            }
+            for (auto& t : th) t.join();
+            for (auto& e : errs) if (e.code) throw e;
+            double ms = 0.0;
+            for (auto& s1 : sts) { merge_stats(st, s1); ms = std::max(ms, s1.fit_kernel_ms); }
+            st.fit_kernel_ms = ms;      // concurrent devices: the slowest one
+        }
         if (stats) *stats = st;
         if (st.failed_sets > 0) return fail(SCDD_ERR_FIT_FAILED, "some fit-sets had no valid model (constant values?)");
         return SCDD_OK;

@@ -259,6 +259,17 @@ def test_sharded_path_two_shards_on_one_device(golden_dir):
     assert np.array_equal(pstream, pstream1)
     adj1, _ = hp.perm_bf(logy[:off[20]], c01[:off[20]], off[:21], 34, seed6=seeds[:20], cdr=cdr[:off[20]], cfg=cfg)
     assert np.array_equal(adj1, adj2)
+    # observed fits: contiguous gene ranges per device, same results
+    Xo, _ = _load(golden_dir, "scDatEx.npz", genes=slice(0, 300))
+    lo, co, oo = hp.gene_csr(Xo, cond)
+    f1 = hp.fit_observed(lo, co, oo, cfg=cfg)
+    try:
+        hp.set_devices([0, 0])
+        f2 = hp.fit_observed(lo, co, oo, cfg=cfg)
+    finally:
+        hp.set_devices([0])
+    assert f1[0].tobytes() == f2[0].tobytes() and np.array_equal(f1[1], f2[1]) and np.array_equal(f1[2], f2[2])
+    assert np.array_equal(f1[3], f2[3]) and np.array_equal(f1[4], f2[4]) and f2[5]["fit_sets"] == 900
     hp.release_cache()                                          # and the library still works afterwards
     again, _ = hp.perm_bf(logy, c01, off, 3, seed6=seeds, cfg=cfg)
     assert np.array_equal(again, one[:, :3])
@@ -308,3 +319,26 @@ def test_permutation_kernel_group_sizes_draw_identical_permutations(ncells, monk
         pi = np.concatenate([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), B)[0].ravel() for g in range(ng)])
         host, _ = hp.perm_bf(logy, c01, off, B, perm_idx=pi, cfg=hp.make_cfg(**PRIORS))
         assert np.array_equal(outs[0], host)
+
+
+def test_scdd_categories_on_the_simulated_example(golden_dir):
+    """scDD(permutations = 100) on scDatExSim through the host mirror, classifyDD included: the row names carry the
+    simulated pattern (DE1..5, DP6..10, DM11..15, DB16..20, EP21..25, EE26..30; R/ex-data.R:76-91), so most DD genes
+    must come out with a DD pattern and most EE / EP genes as not significant"""
+    from scdd_b200 import api
+    d = np.load(os.path.join(golden_dir, "scDatExSim.npz"), allow_pickle=True)
+    X, cond = d["normcounts"], d["condition"]
+    sce = api.SingleCellExperiment({"normcounts": X}, {"condition": cond}, rownames=[str(g) for g in d["genes"]])
+    out = api.scDD(sce, prior_param=dict(alpha=0.01, mu0=0, s0=0.01, a0=0.01, b0=0.01), permutations=100,
+                   testZeroes=False, param={"RNGseed": 816}, verbose=False)
+    cats = api.results(out, "Genes")["DDcategory"]
+    assert all(c in ("DE", "DP", "DM", "DB", "NC", "NS") for c in cats)
+    assert sum(c in ("DE", "DP", "DM", "DB") for c in cats[:20]) >= 12
+    assert sum(c == "NS" for c in cats[20:]) >= 7
+    # classify=False leaves the genes the reference hands to classifyDD unlabelled
+    sce2 = api.SingleCellExperiment({"normcounts": X}, {"condition": cond})
+    out2 = api.scDD(sce2, prior_param=dict(alpha=0.01, mu0=0, s0=0.01, a0=0.01, b0=0.01), permutations=100,
+                    testZeroes=False, param={"RNGseed": 816}, verbose=False, classify=False)
+    cats2 = api.results(out2, "Genes")["DDcategory"]
+    assert [c for c in cats2 if c is not None] == [c for c, c2 in zip(cats, cats2) if c2 is not None]
+    assert np.array_equal(api.results(out, "Genes")["nonzero.pvalue"], api.results(out2, "Genes")["nonzero.pvalue"])
