@@ -498,9 +498,17 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
                     accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
                 }
             } else {
+                // CTA teams: the slab may live in global memory (L2) -- fit-sets beyond 16k points, all of config 5 --
+                // so the loads run two points ahead of the arithmetic instead of opening every iteration with an
+                // L2 round trip
+                double x0 = (px < pend) ? *px : 0.0;
+                double x1 = (px + NT < pend) ? px[NT] : 0.0;
 #pragma unroll 1
-                for (; px < pend; px += NT) {
-                    double x[1] = {*px};
+                while (px < pend) {
+                    double x[1] = {x0};
+                    x0 = x1;
+                    px += NT;
+                    if (px + NT < pend) x1 = px[NT];
                     accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
                 }
             }

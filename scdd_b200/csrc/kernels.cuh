@@ -284,8 +284,10 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
                 refill(act && i < n && used == PG_BLOCK);
                 if (leader && act && i < n) {
                     // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
-                    if (n <= 32768u) {
-                        // ceil(log2 m) <= 15: one 16-bit chunk per attempt, everything fits 32-bit arithmetic
+                    if (bits <= 15) {
+                        // ceil(log2 m) <= 15 (m <= 32768; bits only shrinks while a permutation is drawn, so a gene of up
+                        // to 65535 cells spends three quarters of its picks here): one 16-bit chunk per attempt,
+                        // everything fits 32-bit arithmetic
                         uint32_t mask = (1u << bits) - 1u;
                         // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the active range
                         // receives y[i]: the array ends up holding the permutation reversed.
@@ -315,7 +317,7 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
                     } else {
                         const uint64_t one = 1;
                         uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
-                        while (i < n && used < PG_BLOCK) {
+                        while (i < n && used < PG_BLOCK && bits > 15) {
                             vacc = 65536ULL * vacc + (uint64_t)cand[used++];
                             if (--need == 0) {
                                 uint64_t v = vacc & mask;
