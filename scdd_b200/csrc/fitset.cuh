@@ -362,25 +362,30 @@ __device__ __forceinline__ double reduce16(double (&v)[16], int lane) {
 }
 __device__ __forceinline__ double slot(double t, int e) { return __shfl_sync(FULLMASK, t, 2 * e); }
 
-// A fit-set is executed by a "team": one warp (TW = 1; the vector lives in the warp's shared-memory slab) or a
-// whole CTA of TW warps (large vectors; shared or global memory).  Every thread of a team follows the same
-// control flow on identical reduced values, so team-wide barriers inside the fit are legal.
+// A fit-set is executed by a "team": one warp (TW = 1; the vector lives in the warp's shared-memory slab) or TW warps
+// of a CTA (large vectors; shared or global memory).  A CTA of 16 warps holds 16 / TW teams; teams of several warps
+// synchronise on their own named barrier (id 1 + team index), so the teams of a CTA run independent fit-sets.
+// Every thread of a team follows the same control flow on identical reduced values, so team-wide barriers inside the
+// fit are legal.
 template <int TW>
 struct Team {
     static constexpr int NT = 32 * TW;
-    __device__ __forceinline__ static int tid(int lane) { return TW == 1 ? lane : (int)threadIdx.x; }
+    __device__ __forceinline__ static int index() { return TW == 1 ? (int)(threadIdx.x >> 5) : (int)threadIdx.x / NT; }
+    __device__ __forceinline__ static int tid(int lane) { return TW == 1 ? lane : (int)threadIdx.x % NT; }
+    __device__ __forceinline__ static int warp() { return TW == 1 ? 0 : ((int)(threadIdx.x >> 5)) % TW; }   // warp within the team
     __device__ __forceinline__ static void sync() {
-        if (TW == 1) __syncwarp(); else __syncthreads();
+        if (TW == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + index()), "n"(NT) : "memory");
     }
-    __device__ __forceinline__ static bool lead() { return TW == 1 || (threadIdx.x >> 5) == 0; }
+    __device__ __forceinline__ static bool lead() { return TW == 1 || warp() == 0; }
     // all-reduce of 16 slots: afterwards lane L of EVERY warp holds the team total of slot (L >> 1)
     __device__ __forceinline__ static double reduce(double (&v)[16], int lane, double* red) {
         double t = reduce16(v, lane);
         if (TW > 1) {
-            const int w = threadIdx.x >> 5;
-            __syncthreads();
+            const int w = warp();
+            sync();
             if ((lane & 1) == 0) red[w * 16 + (lane >> 1)] = t;
-            __syncthreads();
+            sync();
             double s = 0.0;
 #pragma unroll 1
             for (int k = 0; k < TW; k++) s += red[k * 16 + (lane >> 1)];

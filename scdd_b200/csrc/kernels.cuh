@@ -456,7 +456,8 @@ inline cudaError_t init_exp_table() {
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(LOG_TABLE_GLOBAL, log_table_host(), SCDD_LOG_TABLE_SIZE * sizeof(LogTab));
 }
-constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant
+constexpr int FIT_CTA_WARPS = SCDD_FIT_WARPS;     // team size of the CTA-per-fit-set variant (few, very large fit-sets)
+constexpr int FIT_SUB_WARPS = 4;                   // team size of the default multi-warp variant: 4 teams per CTA
 constexpr int FIT_WARP_TEAM_MAX_POINTS = 2048;
 constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8 + SCDD_LOG_TABLE_SIZE * 16;   // the CTA's 2^(j/2048) table (16 KB of static shared memory)    // larger fit-sets are run by a whole CTA
 
@@ -469,7 +470,12 @@ __host__ __device__ constexpr size_t fit_region_head(int tw) {
 __host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
     return fit_region_head(1) + (size_t)np * sizeof(double);
 }
-static_assert(fit_region_head(1) % 16 == 0 && fit_region_head(FIT_CTA_WARPS) % 16 == 0, "xs must stay 16-byte aligned");
+static_assert(fit_region_head(1) % 16 == 0 && fit_region_head(FIT_CTA_WARPS) % 16 == 0 &&
+              fit_region_head(FIT_SUB_WARPS) % 16 == 0, "xs must stay 16-byte aligned");
+// bytes of one team's region when the CTA holds 16 / tw teams: head, plus the slab when it is kept in shared memory
+__host__ __device__ constexpr size_t fit_team_region(int tw, int np, bool slab_in_smem) {
+    return fit_region_head(tw) + (slab_in_smem ? (size_t)np * sizeof(double) : 0);
+}
 
 // BUDGET: pass 1 of a two-pass launch (see FitArgs::iter_budget).  A separate instantiation, so that the kernel of the
 // permutation chunks is compiled exactly as if the budget logic did not exist.
@@ -482,12 +488,13 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     for (int i = threadIdx.x; i < SCDD_EXP_TABLE_SIZE; i += blockDim.x) EXP_TABLE_SH[i] = EXP_TABLE_GLOBAL[i];   // 2^(j/2048)
     for (int i = threadIdx.x; i < SCDD_LOG_TABLE_SIZE; i += blockDim.x) LOG_TABLE_SH[i] = LOG_TABLE_GLOBAL[i];
     __syncthreads();
-    unsigned char* region = smem_raw + (TW == 1 ? warp * fit_smem_per_warp(a.np_max) : 0);
+    const int team = T::index(), teams = FIT_MAX_WARPS / TW;
+    unsigned char* region = smem_raw + (size_t)team * fit_team_region(TW, a.np_max, TW == 1 || a.xs_global == nullptr);
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
     Row* rows = reinterpret_cast<Row*>(reinterpret_cast<unsigned char*>(pm + 4 * GMAX) + sizeof(EmCtx));   // EmCtx sits between them
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
     double* red = reinterpret_cast<double*>(st + 1);
-    double* xs = (TW > 1 && a.xs_global) ? a.xs_global + (size_t)blockIdx.x * a.np_max
+    double* xs = (TW > 1 && a.xs_global) ? a.xs_global + ((size_t)blockIdx.x * teams + team) * a.np_max
                                          : reinterpret_cast<double*>(region + fit_region_head(TW));
     const bool lead0 = T::lead() && lane == 0;
     if (lead0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -501,11 +508,11 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ULL);
             item = __shfl_sync(FULLMASK, item, 0);
         } else {
-            __syncthreads();
-            if (threadIdx.x == 0) *reinterpret_cast<long long*>(red) = (long long)atomicAdd(a.work_counter, 1ULL);
-            __syncthreads();
+            T::sync();
+            if (tid == 0) *reinterpret_cast<long long*>(red) = (long long)atomicAdd(a.work_counter, 1ULL);
+            T::sync();
             item = *reinterpret_cast<long long*>(red);
-            __syncthreads();
+            T::sync();
         }
         if (item >= total) break;
         if (a.only_deferred && !a.deferred[item]) continue;

@@ -317,7 +317,7 @@ struct Pipeline {
         a.stats = d_stats.p;
         a.cfg = cfg;
         a.xs_global = nullptr;
-        int grid, threads;
+        int grid, threads, tw = 1;
         size_t smem;
         const bool warp_team = nmax_points <= FIT_WARP_TEAM_MAX_POINTS && !force_cta;
         if (warp_team) {
@@ -329,25 +329,34 @@ struct Pipeline {
             if (a.iter_budget) CK(cudaFuncSetAttribute(fit_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else CK(cudaFuncSetAttribute(fit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         } else {
-            // one CTA per fit-set; the vector stays in shared memory when it fits, else in an L2-resident slab
-            const size_t head = fit_region_head(FIT_CTA_WARPS);
-            threads = FIT_CTA_WARPS * 32;
-            grid = (int)std::min<long long>(n_sm, total);
-            if (head + (size_t)np * sizeof(double) <= smem_cap) {
-                smem = head + (size_t)np * sizeof(double);
+            // several warps per fit-set.  Default: the whole CTA (16 warps) per fit-set -- the slabs of 148 concurrent
+            // fit-sets of config-5 size (352 KB each) stay L2-resident, and the two-pass observed fits are bound by
+            // their longest single fit-set.  4-warp teams, four to a CTA, only for bulk work on mid-size vectors whose
+            // slabs all fit shared memory (measured in round 2, profiles/sub_cta_teams_r02.txt: with 4-warp teams
+            // config 5 drops from 0.377 to 0.250 of peak -- 592 slabs no longer fit L2 -- and the observed-fit tail grows)
+            const bool bulk_mid = np <= 4096 && total > 8LL * n_sm && !a.only_deferred &&
+                                  fit_team_region(FIT_SUB_WARPS, np, true) * (FIT_MAX_WARPS / FIT_SUB_WARPS) <= smem_cap;
+            tw = bulk_mid ? FIT_SUB_WARPS : FIT_CTA_WARPS;
+            const int teams = FIT_MAX_WARPS / tw;
+            threads = FIT_MAX_WARPS * 32;
+            grid = (int)std::min<long long>(n_sm, (total + teams - 1) / teams);
+            if (fit_team_region(tw, np, true) * teams <= smem_cap) {
+                smem = fit_team_region(tw, np, true) * teams;
             } else {
-                smem = head;
-                const size_t need = (size_t)grid * np;
+                smem = fit_team_region(tw, np, false) * teams;
+                const size_t need = (size_t)grid * teams * np;
                 if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
                 a.xs_global = d_xs_scratch.p;
             }
-            CK(cudaFuncSetAttribute(fit_kernel<FIT_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (tw == FIT_SUB_WARPS) CK(cudaFuncSetAttribute(fit_kernel<FIT_SUB_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CK(cudaFuncSetAttribute(fit_kernel<FIT_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         CK(cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), s));
         Timed t;
         if (time_kernels) t = tick_begin(0, s);
         if (warp_team && a.iter_budget) fit_kernel<1, true><<<grid, threads, smem, s>>>(a);
         else if (warp_team) fit_kernel<1><<<grid, threads, smem, s>>>(a);
+        else if (tw == FIT_SUB_WARPS) fit_kernel<FIT_SUB_WARPS><<<grid, threads, smem, s>>>(a);
         else fit_kernel<FIT_CTA_WARPS><<<grid, threads, smem, s>>>(a);
         CK(cudaGetLastError());
         if (time_kernels) tick_end(t, s);

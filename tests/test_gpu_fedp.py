@@ -116,8 +116,16 @@ def test_scdd_categories_through_the_api(golden_dir):
     G = api.results(out, "Genes")
     cats = G["DDcategory"]
     padj = G["nonzero.pvalue.adj"]
-    assert all(c is None for c, p in zip(cats, padj) if p < 0.05)          # significant -> classifyDD (R)
-    assert set(c for c in cats if c is not None) <= {"NS", "DP", "NC"}
+    # significant genes get classifyDD's pattern; the others come out of feDP as NS / DP, or as classifyDD's verdict
+    # on feDP's "NC" candidates
+    assert all(c in ("DE", "DP", "DM", "DB", "NC") for c, p in zip(cats, padj) if p < 0.05)
+    assert set(cats) <= {"NS", "DE", "DP", "DM", "DB", "NC"}
+    # classify=False: exactly the genes the reference hands to classifyDD stay unlabelled
+    out0 = api.scDD(api.SingleCellExperiment({"normcounts": X}, {"condition": cond}), prior_param=pri, permutations=20,
+                    testZeroes=False, param={"RNGseed": 7}, verbose=False, classify=False)
+    cats0 = api.results(out0, "Genes")["DDcategory"]
+    assert all(c is None for c, p in zip(cats0, padj) if p < 0.05)
+    assert set(c for c in cats0 if c is not None) <= {"NS", "DP"}
 
 
 def test_scdd_with_filtered_and_constant_genes():

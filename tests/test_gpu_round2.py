@@ -342,3 +342,26 @@ def test_scdd_categories_on_the_simulated_example(golden_dir):
     cats2 = api.results(out2, "Genes")["DDcategory"]
     assert [c for c in cats2 if c is not None] == [c for c, c2 in zip(cats, cats2) if c2 is not None]
     assert np.array_equal(api.results(out, "Genes")["nonzero.pvalue"], api.results(out2, "Genes")["nonzero.pvalue"])
+
+
+def test_mid_size_bulk_fit_sets_on_four_warp_teams():
+    """bulk work on 2,049..4,096-point fit-sets runs on 4-warp teams, four to a CTA on their own named barriers
+    (Team<4>): 60 genes x 10 permutations x 2 halves of ~2,600 points = 1,200 fit-sets (> 8 per SM)"""
+    rng = np.random.default_rng(77)
+    rows, conds = [], []
+    for g in range(60):
+        n = 5000 + int(rng.integers(0, 600))
+        a = rng.normal(2.0, 0.6, size=int(n * (0.3 + 0.4 * rng.random())))
+        b = rng.normal(4.0 + rng.random(), 0.5, size=n - a.size)
+        v = np.concatenate([a, b])
+        rng.shuffle(v)
+        rows.append(v)
+        conds.append((rng.random(n) < 0.5).astype(np.int32))
+    off = np.r_[0, np.cumsum([r.size for r in rows])].astype(np.int64)
+    logy, c01 = np.concatenate(rows), np.concatenate(conds)
+    seeds = hp.gene_seeds(4, 60)
+    out, st, terms = hp.perm_bf(logy, c01, off, 10, seed6=seeds, cfg=hp.make_cfg(**PRIORS), return_terms=True)
+    ref = po.perm_batch_ex(logy, c01, off, 10, seed6=seeds, cfg=po.make_cfg(**PRIORS))
+    assert st["fit_sets"] == 1200 and st["failed_sets"] == 0
+    np.testing.assert_allclose(terms, ref["jp_terms"], rtol=RTOL)
+    np.testing.assert_allclose(out, ref["bf_perm"], rtol=RTOL)
