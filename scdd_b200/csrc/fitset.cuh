@@ -504,16 +504,17 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
                 }
             } else {
                 // CTA teams: the slab may live in global memory (L2) -- fit-sets beyond 16k points, all of config 5 --
-                // so the loads run two points ahead of the arithmetic instead of opening every iteration with an
+                // so the loads run three points ahead of the arithmetic instead of opening every iteration with an
                 // L2 round trip
                 double x0 = (px < pend) ? *px : 0.0;
                 double x1 = (px + NT < pend) ? px[NT] : 0.0;
+                double x2 = (px + 2 * NT < pend) ? px[2 * NT] : 0.0;
 #pragma unroll 1
                 while (px < pend) {
                     double x[1] = {x0};
-                    x0 = x1;
+                    x0 = x1; x1 = x2;
                     px += NT;
-                    if (px + NT < pend) x1 = px[NT];
+                    if (px + 2 * NT < pend) x2 = px[2 * NT];
                     accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
                 }
             }
@@ -1140,6 +1141,50 @@ __device__ __forceinline__ void team_sort(double* xs, int np, int lane) {
             }
             T::sync();
         }
+    }
+}
+
+// The same network for a slab in global memory (CTA teams on vectors beyond shared memory: config 5), tile by tile
+// through shared memory: compare-exchanges at distance j < TILE stay inside one TILE-aligned block, so every stage
+// with j < TILE runs on a tile resident in shared memory and only the stages with j >= TILE touch global memory
+// (np = 65,536, TILE = 16,384: 3 global stages and 3 residencies per tile instead of 136 global stages; ncu had the
+// all-global sort at 11 % of the config-5 kernel, 82 % of it long-scoreboard stalls).
+template <int TW>
+__device__ __forceinline__ void team_sort_tiled(double* xs, int np, int lane, double* tile, int TILE) {
+    typedef Team<TW> T;
+    const int tid = T::tid(lane);
+    auto local = [&](int base, int k_lo, int k_hi, int j_top) {
+        // tile [base, base + TILE): stages (k, j) for k = k_lo..k_hi, j from min(k/2, j_top) down to 1
+        for (int t = tid; t < TILE; t += T::NT) tile[t] = xs[base + t];
+        T::sync();
+        for (int k = k_lo; k <= k_hi; k <<= 1) {
+            for (int j = min(k >> 1, j_top); j > 0; j >>= 1) {
+                for (int t = tid; t < (TILE >> 1); t += T::NT) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const bool up = (((base + i) & k) == 0);
+                    const double a = tile[i], b = tile[l];
+                    if ((a > b) == up) { tile[i] = b; tile[l] = a; }
+                }
+                T::sync();
+            }
+        }
+        for (int t = tid; t < TILE; t += T::NT) xs[base + t] = tile[t];
+        T::sync();
+    };
+    for (int base = 0; base < np; base += TILE) local(base, 2, TILE, TILE >> 1);          // every k <= TILE
+    for (int k = TILE << 1; k <= np; k <<= 1) {
+        for (int j = k >> 1; j >= TILE; j >>= 1) {                                         // global stages
+            for (int t = tid; t < (np >> 1); t += T::NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = ((i & k) == 0);
+                const double a = xs[i], b = xs[l];
+                if ((a > b) == up) { xs[i] = b; xs[l] = a; }
+            }
+            T::sync();
+        }
+        for (int base = 0; base < np; base += TILE) local(base, k, k, TILE >> 1);          // the stages j < TILE of this k
     }
 }
 

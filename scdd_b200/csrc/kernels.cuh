@@ -407,7 +407,8 @@ struct FitArgs {
     int perm_b0;               // first permutation of this launch inside `perm`
     int ngenes, nb, sets;      // sets per (gene, permutation): 2 = (c1, c2), 3 = (c1, c2, oa)
     int np_max;                // slab capacity (power of two)
-    double* xs_global;         // CTA teams only: per-CTA slabs in global memory when np_max exceeds shared memory
+    double* xs_global;         // CTA teams only: per-team slabs in global memory when np_max exceeds shared memory
+    int sort_tile;             // ... then the sort runs through a shared-memory tile of this many doubles per team (0: none)
     const int32_t* gene_order; // nullable: genes in decreasing expected cost (longest-processing-time-first)
     double* gene_cost;         // nullable: [ngenes] accumulated EM work (triples) per gene, feeds gene_order
     double* jp;                // [ngenes * nb * sets] log joint posterior of each fit-set
@@ -489,7 +490,9 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     for (int i = threadIdx.x; i < SCDD_LOG_TABLE_SIZE; i += blockDim.x) LOG_TABLE_SH[i] = LOG_TABLE_GLOBAL[i];
     __syncthreads();
     const int team = T::index(), teams = FIT_MAX_WARPS / TW;
-    unsigned char* region = smem_raw + (size_t)team * fit_team_region(TW, a.np_max, TW == 1 || a.xs_global == nullptr);
+    const size_t stride = (TW == 1 || a.xs_global == nullptr) ? fit_team_region(TW, a.np_max, true)
+                                                              : fit_region_head(TW) + (size_t)a.sort_tile * sizeof(double);
+    unsigned char* region = smem_raw + (size_t)team * stride;
     double* pm = reinterpret_cast<double*>(region);               // {mu, nh, lc, pad} x GMAX, 16-byte aligned
     Row* rows = reinterpret_cast<Row*>(reinterpret_cast<unsigned char*>(pm + 4 * GMAX) + sizeof(EmCtx));   // EmCtx sits between them
     WarpStats* st = reinterpret_cast<WarpStats*>(rows + GMAX);
@@ -543,7 +546,10 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
             xs[j] = v;
         }
         T::sync();
-        team_sort<TW>(xs, np, lane);
+        if (TW > 1 && a.xs_global && a.sort_tile > 0 && np > a.sort_tile)
+            team_sort_tiled<TW>(xs, np, lane, reinterpret_cast<double*>(region + fit_region_head(TW)), a.sort_tile);
+        else
+            team_sort<TW>(xs, np, lane);
 
         double jp = NaN;
         int comps = 0;

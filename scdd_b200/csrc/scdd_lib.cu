@@ -317,6 +317,7 @@ struct Pipeline {
         a.stats = d_stats.p;
         a.cfg = cfg;
         a.xs_global = nullptr;
+        a.sort_tile = 0;
         int grid, threads, tw = 1;
         size_t smem;
         const bool warp_team = nmax_points <= FIT_WARP_TEAM_MAX_POINTS && !force_cta;
@@ -343,7 +344,13 @@ struct Pipeline {
             if (fit_team_region(tw, np, true) * teams <= smem_cap) {
                 smem = fit_team_region(tw, np, true) * teams;
             } else {
-                smem = fit_team_region(tw, np, false) * teams;
+                // slab per team in global memory (L2); the sort goes through the largest power-of-two tile that fits
+                // the team's share of shared memory
+                const size_t head = fit_team_region(tw, np, false);
+                int tile = 1;
+                while ((size_t)tile * 2 * sizeof(double) + head <= smem_cap / teams) tile <<= 1;
+                a.sort_tile = (tile >= 1024 && tile < np) ? tile : 0;
+                smem = (head + (size_t)a.sort_tile * sizeof(double)) * teams;
                 const size_t need = (size_t)grid * teams * np;
                 if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
                 a.xs_global = d_xs_scratch.p;
