@@ -206,6 +206,28 @@ int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, in
 int32_t scdd_cluster_counts(const int32_t* labels, const int32_t* cond01, const int64_t* gene_off, int32_t ngenes,
                             int32_t min_size, int32_t which, int32_t* counts);
 
+/* ---- testZeroes, R/classify.dd.R:262-286 ----
+ * Per gene with at least one zero: arm::bayesglm(y > 0 ~ detection + factor(cond), binomial(logit)) and the Wald
+ * p-value of the condition coefficient, summary(M1)$coefficients[3, 4]; NaN (R's NA) for a gene without zeros (:267).
+ * detection = colSums(X > 0) / nrow(X) over ALL ngenes rows (:263).  cell_level2[ncells]: 1 where the cell belongs to
+ * the SECOND level of factor(cond) (levels are sort(unique(cond)) -- not scDD()'s `ref`); the posterior mode depends
+ * on which level is the baseline because the intercept has its own prior.  these[nthese]: 0-based rows to test
+ * (NULL = rows 0..nthese-1).  The host packs one bit per cell and gene in a threaded pass over X; the regressions run
+ * on the first device of scdd_set_devices (they cost milliseconds, see scdd_b200/csrc/zeroes.cuh).
+ * detail (nullable) [nthese*8]: coef[3], se[3], iterations, deviance.  Options follow bayesglm()'s defaults. */
+typedef struct {
+    double prior_scale;                 /* 2.5  (predictors; divided by max-min for a two-valued, 2 sd for another predictor) */
+    double prior_scale_for_intercept;   /* 10   */
+    double prior_df;                    /* 1    (Cauchy; also for the intercept) */
+    double epsilon;                     /* 1e-8 glm.control */
+    int32_t maxit;                      /* 100  */
+    int32_t reserved;
+} scdd_glm_opts;
+void scdd_default_glm_opts(scdd_glm_opts* opts);
+int32_t scdd_test_zeroes(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_level2,
+                         const int32_t* these, int64_t nthese, const scdd_glm_opts* opts, double* pvalue,
+                         double* detail, scdd_stats* stats);
+
 /* ---- device-resident plan (throughput harness; inputs stay in HBM between steps) ---- */
 typedef struct scdd_plan scdd_plan;
 /* uploads the gene block to `device`, runs the per-gene preparation kernels.

@@ -1,7 +1,8 @@
 # scDD_b200.R -- drop-in dispatcher: scDD() with the reference's exact signature, argument checks, messages and result
 # objects (R/scDD.R:217-602), with the per-gene work of the hot path done by libscdd_b200.so through the helpers of
 # scDD_gpu.R.  A maintainer replaces the body of R/scDD.R by this file (or sources it after the package) -- nothing
-# else of the package changes: classifyDD(), testZeroes(), testKS()'s wrapper, results() are the reference's own.
+# else of the package changes: classifyDD() and results() are the reference's own; testKS() and testZeroes() are
+# redefined at the end of this file with the reference's signatures.
 #
 # Written from the reference's behaviour, not from its text: the three bplapply fan-outs and the per-gene R loops are
 # gone, so the function is organised around flat vectors (one CSR block for all fitted genes) instead of lists.
@@ -117,7 +118,7 @@ scDD <- function(SCdat,
     cats.all[tofit] <- cats
   }
 
-  ## ---- zero test: the reference's own (arm::bayesglm) ----
+  ## ---- zero test: the Bayesian logistic regressions of arm::bayesglm as one kernel (testZeroes below) ----
   pvals.z <- rep(NA, nrow(X))
   if (testZeroes) {
     pvals.z <- testZeroes(X, cond)
@@ -184,3 +185,7 @@ testKS <- function(dat, condition, inclZero = TRUE, numDE = NULL, DEIndex) {
   }
   list(genes = sig_genes_ks, p = ks.pval, p.unadj = ks.pval.unadj)
 }
+
+# testZeroes() with the reference's signature and return value (R/classify.dd.R:262-286): the unadjusted p-value of the
+# condition coefficient per gene of `these`, NA for a gene without zeros
+testZeroes <- function(dat, cond, these = 1:nrow(dat)) testZeroes_gpu(as.matrix(dat), cond, these)

@@ -124,6 +124,13 @@ feDP_gpu <- function(g, fit, sig_genes, nrow_pe, cdr = NULL, testZeroes = FALSE,
   pval.ns
 }
 
+# replaces the bplapply of arm::bayesglm fits inside testZeroes, R/classify.dd.R:262-286.  factor(cond) sorts its
+# levels, so the baseline of the condition dummy is the smallest label -- not scDD()'s `ref` (first seen).
+testZeroes_gpu <- function(dat, cond, these = seq_len(nrow(dat))) {
+  storage.mode(dat) <- "double"
+  .Call(C_scdd_test_zeroes, dat, nrow(dat), ncol(dat), as.integer(factor(cond)) - 1L, as.integer(these))
+}
+
 # BiocParallel::register(param) of R/scDD.R:314 becomes a device list
 scdd_set_devices <- function(devices = NULL) invisible(.Call(C_scdd_set_devices, if (is.null(devices)) NULL else as.integer(devices)))
 scdd_device_count <- function() .Call(C_scdd_device_count)

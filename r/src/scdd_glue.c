@@ -188,6 +188,25 @@ SEXP C_scdd_cell_covariate(SEXP dat, SEXP nrow, SEXP ncol, SEXP values, SEXP off
     return out;
 }
 
+/* testZeroes, R/classify.dd.R:262-286: per row of `these` (1-based) the Wald p-value of the condition coefficient of
+ * arm::bayesglm(y > 0 ~ detection + factor(cond), binomial); level2 = as.integer(factor(cond)) - 1L; NA for a gene
+ * without zeros.  One kernel for all genes instead of a bplapply of bayesglm calls. */
+SEXP C_scdd_test_zeroes(SEXP dat, SEXP nrow, SEXP ncol, SEXP level2, SEXP these) {
+    int ng = asInteger(nrow), nc = asInteger(ncol);
+    need_type(dat, REALSXP, "dat"); need_type(level2, INTSXP, "level2"); need_type(these, INTSXP, "these");
+    if (ng < 0 || nc < 0 || XLENGTH(dat) != (R_xlen_t)ng * nc || LENGTH(level2) != nc)
+        Rf_error("scdd_b200: dat must be a genes x cells double matrix with one condition entry per cell");
+    int n = LENGTH(these);
+    int32_t *rows = (int32_t *)R_alloc(n > 0 ? n : 1, sizeof(int32_t));
+    for (int j = 0; j < n; j++) rows[j] = INTEGER(these)[j] - 1;
+    SEXP out = PROTECT(allocVector(REALSXP, n));
+    int rc = scdd_test_zeroes(REAL(dat), ng, nc, 1, INTEGER(level2), rows, n, NULL, REAL(out), NULL, NULL);
+    if (rc != SCDD_OK) { UNPROTECT(1); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    for (int j = 0; j < n; j++) if (ISNAN(REAL(out)[j])) REAL(out)[j] = NA_REAL;
+    UNPROTECT(1);
+    return out;
+}
+
 /* the per-gene filters of scDD() in one threaded pass over the matrix: nonzero cells per condition (tofit,
  * R/scDD.R:270-274), "all nonzero values of that condition identical" flags (skipConstant, :292-298) and the number of
  * negative entries (:262) */
@@ -275,6 +294,7 @@ static const R_CallMethodDef calls[] = {
     {"C_scdd_zhat", (DL_FUNC)&C_scdd_zhat, 8},
     {"C_scdd_cluster_counts", (DL_FUNC)&C_scdd_cluster_counts, 5},
     {"C_scdd_fedp", (DL_FUNC)&C_scdd_fedp, 7},
+    {"C_scdd_test_zeroes", (DL_FUNC)&C_scdd_test_zeroes, 5},
     {"C_scdd_device_count", (DL_FUNC)&C_scdd_device_count, 0},
     {NULL, NULL, 0}};
 

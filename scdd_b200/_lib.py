@@ -62,11 +62,18 @@ FIT_DTYPE = np.dtype([("G", np.int32), ("model_v", np.int32), ("n", np.int32), (
                       ("bic", np.float64), ("loglik", np.float64), ("mean", np.float64, (GMAX,)),
                       ("var", np.float64, (GMAX,))])
 
+class GlmOpts(C.Structure):
+    """scdd_glm_opts of include/scdd_b200.h"""
+    _fields_ = [("prior_scale", C.c_double), ("prior_scale_for_intercept", C.c_double), ("prior_df", C.c_double),
+                ("epsilon", C.c_double), ("maxit", C.c_int32), ("reserved", C.c_int32)]
+
+
 EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set_devices", "scdd_default_cfg",
            "scdd_fit_observed", "scdd_perm_bf", "scdd_perm_bf_ex", "scdd_release_cache", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
            "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax", "scdd_selftest_log",
-           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_dense_cell_covariate", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p"]
+           "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_dense_cell_covariate", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p",
+           "scdd_default_glm_opts", "scdd_test_zeroes"]
 
 
 def lib_path():
@@ -120,6 +127,9 @@ def lib():
     L.scdd_cluster_counts.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.scdd_fedp.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(Stats)]
     L.scdd_selftest_student_p.argtypes = [vp, vp, C.c_int32, vp]
+    L.scdd_default_glm_opts.argtypes = [C.POINTER(GlmOpts)]
+    L.scdd_default_glm_opts.restype = None
+    L.scdd_test_zeroes.argtypes = [vp, i64, i64, C.c_int32, vp, vp, i64, C.POINTER(GlmOpts), vp, vp, C.POINTER(Stats)]
     _LIB = L
     return L
 

@@ -15,9 +15,8 @@ All numerical work of the hot path happens in libscdd_b200.so (CUDA); this modul
                                       its Monte-Carlo test uses numpy's Student-t draws, not R's stream -- same
                                       distribution, borderline genes may differ as between two R seeds)
 
-What stays in R and is NOT reproduced here: testZeroes (arm::bayesglm; SURVEY section 2, out of scope; the benchmark
-configs use testZeroes=FALSE).  With the R shim (r/R/scDD_b200.R) the reference's own classifyDD and testZeroes run
-on the lists this path produces.
+testZeroes (R/classify.dd.R:262-286, arm::bayesglm) runs on the device as well (csrc/zeroes.cuh): scDD(testZeroes=True)
+adds the DZ category, the zero.pvalue columns and Fisher's combined p-value exactly as R/scDD.R:517-526, :568-588.
 """
 import numpy as np
 
@@ -92,6 +91,37 @@ def testKS(dat, condition, inclZero=True, numDE=None, DEIndex=None, rownames=Non
         out["power"] = sum(1 for i in sig1 if i in de) / numDE
         out["fdr"] = (sum(1 for i in sig1 if i not in de) / len(sig1)) if sig1 else float("nan")
     return out
+
+
+def testZeroes(dat, cond, these=None):
+    """R/classify.dd.R:262-286: p-value of a difference in the proportion of zeroes between conditions that the
+    detection rate does not explain (Bayesian logistic regression, one device kernel for all genes).  dat: genes x
+    cells on the original scale; these: 0-based rows (R's `these` is 1-based).  NaN = NA (gene without zeros)."""
+    return hp.test_zeroes(dat, cond, these=these)[0]
+
+
+testZeroes.__test__ = False
+
+
+def fishersCombinedPval(x):
+    """R/scDD.R:570-578, one row of cbind(pvals.all, pvals.z).  pchisq(-2 sum(log x), df = 4, lower = FALSE) has the
+    closed form P (1 - log P), P the product of the two p-values."""
+    x = np.asarray(x, dtype=np.float64)
+    nas = int(np.isnan(x).sum())
+    if nas == 0:
+        with np.errstate(divide="ignore"):
+            h = -float(np.sum(np.log(x)))              # chi-square statistic / 2
+        if np.isinf(h):
+            return 0.0
+        k = len(x)                                     # upper tail of chi-square with 2k df: e^-h sum_{i<k} h^i / i!
+        term, acc = 1.0, 0.0
+        for i in range(k):
+            acc += term
+            term *= h / (i + 1)
+        return float(np.exp(-h) * acc)
+    if nas == 1:
+        return float(x[~np.isnan(x)][0])
+    return float("nan")
 
 
 def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr=None, min_size=3, stats_out=None,
@@ -232,9 +262,6 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         parallelBy = parallelBy[0]
     if parallelBy not in ("Genes", "Permutations"):
         raise ValueError("'arg' should be one of 'Genes', 'Permutations'")
-    if testZeroes:
-        raise NotImplementedError("testZeroes=TRUE needs arm::bayesglm (out of scope of the accelerated path, "
-                                  "SURVEY section 2); the benchmark configs use testZeroes=FALSE")
     X = normcounts(SCdat)
     cond = SCdat.colData.get(condition)
     if cond is None or len(_unique_in_order(cond)) != 2 or len(cond) != X.shape[1]:
@@ -251,13 +278,14 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     need = max(min_size, 2, min_nonzero)
     tofit = np.nonzero((nnz0 >= need) & (nnz1 >= need))[0]
     ngenes = X.shape[0]
+    todo = "Only testing for DZ for these genes." if testZeroes else "Skipping these genes."
+    cut = level / 2 if testZeroes else level            # R/scDD.R:362-366, :475-479, :503-507
     if tofit.size < ngenes:
-        msg(f"Notice: {ngenes - tofit.size} genes have less than {min_nonzero} nonzero cells per condition.  "
-            f"Skipping these genes.")
+        msg(f"Notice: {ngenes - tofit.size} genes have less than {min_nonzero} nonzero cells per condition.  {todo}")
     # genes whose nonzero values are all identical within a condition (R/scDD.R:292-310)
     skip = const0[tofit] | const1[tofit]
     if skip.any():
-        msg(f"Notice: {int(skip.sum())} Genes have constant nonzero values.  Skipping these genes.")
+        msg(f"Notice: {int(skip.sum())} Genes have constant nonzero values.  {todo}")
         tofit = tofit[~skip]
     param = dict(param or {})
     if param.get("devices") is not None:
@@ -290,7 +318,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")
         res_ks = testKS(X if sel is None else X[tofit], cond, inclZero=False)
-        sig = np.nonzero(res_ks["p"] < level)[0]
+        sig = np.nonzero(res_ks["p"] < cut)[0]
         pvals = res_ks["p.unadj"]
     else:
         msg("Performing permutations to evaluate independence of clustering and condition for each gene")
@@ -322,7 +350,8 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         obs = (bf - den) if adjust_perms else bf                      # R/scDD.R:467-473
         pvals = (bf_perm > obs[:, None]).sum(axis=1) / float(permutations)
         pvals = np.where(np.isnan(bf_perm).any(axis=1) | np.isnan(obs), np.nan, pvals)   # R: sum() over an NA is NA
-        sig = np.nonzero(p_adjust_BH(pvals) < level)[0]
+        with np.errstate(invalid="ignore"):
+            sig = np.nonzero(p_adjust_BH(pvals) < cut)[0]
     pvals_all = np.full(ngenes, np.nan)
     pvals_all[tofit] = pvals
     cats_all = [None] * ngenes
@@ -342,11 +371,11 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
                                    cdr=cdr if adjust_perms else None, min_size=min_size, rng=crng, p_shift=p_shift_all)
         else:
             cats[sig] = None
-        ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=False, cdr=cdr if adjust_perms else None,
+        ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=testZeroes, cdr=cdr if adjust_perms else None,
                              min_size=min_size, stats_out=stats.setdefault("feDP", {}), precomputed=fe_all)
         cats[ns] = cat_ns
         with np.errstate(invalid="ignore"):
-            to_classify = np.nonzero((p_adjust_BH(pvals) > level) & (cats == "NC"))[0]
+            to_classify = np.nonzero((p_adjust_BH(pvals) > cut) & (cats == "NC"))[0]
         if classify:
             cats[to_classify] = classifyDD(logy, c01, off, to_classify, cls_oa, cls_c, prior_param,
                                            adjust_perms=adjust_perms, cdr=cdr if adjust_perms else None,
@@ -355,6 +384,19 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
             cats[to_classify] = None
         for j, g in enumerate(tofit):
             cats_all[g] = cats[j]
+    # zero test (R/scDD.R:517-526): DZ for the genes the nonzero test did not categorise, NS for the rest
+    pvals_z = np.full(ngenes, np.nan)
+    if testZeroes:
+        pvals_z, stz = hp.test_zeroes(X, cond)
+        stats["testZeroes"] = stz
+        pz = p_adjust_BH(pvals_z)
+        for g in range(ngenes):
+            if cats_all[g] in ("DE", "DP", "DM", "DB") or np.isnan(pz[g]):
+                continue
+            if pz[g] < level / 2:
+                cats_all[g] = "DZ"
+            elif categorize:
+                cats_all[g] = "NS"
     # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label
     if categorize:
         MAP = hp.labels_to_dense(X, cond, cls_oa, off, genes=tofit, ref=ref)
@@ -371,6 +413,10 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
              "Clusters.combined": _spread(comps_all), "Clusters.c1": _spread(comps_c1),
              "Clusters.c2": _spread(comps_c2), "nonzero.pvalue": pvals_all,
              "nonzero.pvalue.adj": p_adjust_BH(pvals_all)}
+    if testZeroes:                                      # R/scDD.R:568-588
+        comb = np.array([fishersCombinedPval((a, b)) for a, b in zip(pvals_all, pvals_z)])
+        Genes.update({"zero.pvalue": pvals_z, "zero.pvalue.adj": p_adjust_BH(pvals_z),
+                      "combined.pvalue": comb, "combined.pvalue.adj": p_adjust_BH(comb)})
     SCdat.metadata["Genes"] = Genes
     SCdat.metadata["Zhat.combined"] = MAP
     SCdat.metadata["Zhat.c1"] = MAP1

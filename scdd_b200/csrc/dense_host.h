@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -182,6 +183,69 @@ inline bool labels_to_dense(const View& v, const int32_t* cc, int which, const i
                              int64_t g = genes ? genes[j] : j;
                              Z[cm ? g + colmap[c] * ng : g * ncols + colmap[c]] = (double)labels[p];
                          });
+}
+
+// testZeroes marshalling (R/classify.dd.R:263-267): detection[c] = (number of rows with X > 0 in cell c) / nrow over
+// ALL rows; for the selected rows one bit per cell (y > 0; bit c % 32 of word c / 32, W words per row, zeroed here)
+// and the count of exact zeros (the `sum(y == 0) > 0` rule).
+inline void zero_mask(const View& v, const int32_t* genes, int64_t nsel, int64_t W, uint32_t* mask, int32_t* nzero,
+                      double* detection) {
+    std::vector<int64_t> cnt(v.ncells, 0);
+    if (v.col_major) {
+        parallel_ranges(v.ncells, 16, [&](int64_t lo, int64_t hi) {
+            for (int64_t c = lo; c < hi; c++) {
+                const double* col = v.X + c * v.ngenes;
+                int64_t k = 0;
+                for (int64_t g = 0; g < v.ngenes; g++) k += col[g] > 0;
+                cnt[c] = k;
+            }
+        });
+    } else {
+        std::mutex mu;
+        parallel_ranges(v.ngenes, 64, [&](int64_t lo, int64_t hi) {
+            std::vector<int64_t> mine(v.ncells, 0);
+            for (int64_t g = lo; g < hi; g++) {
+                const double* row = v.X + g * v.ncells;
+                for (int64_t c = 0; c < v.ncells; c++) mine[c] += row[c] > 0;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            for (int64_t c = 0; c < v.ncells; c++) cnt[c] += mine[c];
+        });
+    }
+    for (int64_t c = 0; c < v.ncells; c++) detection[c] = (double)cnt[c] / (double)v.ngenes;
+    parallel_ranges(nsel, BLK, [&](int64_t lo, int64_t hi) {
+        for (int64_t b = lo; b < hi; b += BLK) {
+            const int64_t w = std::min(BLK, hi - b);
+            int64_t row[BLK];
+            for (int64_t j = 0; j < w; j++) {
+                row[j] = genes ? genes[b + j] : b + j;
+                nzero[b + j] = 0;
+                std::fill(mask + (b + j) * W, mask + (b + j + 1) * W, 0u);
+            }
+            if (v.col_major) {
+                for (int64_t c = 0; c < v.ncells; c++) {
+                    const double* col = v.X + c * v.ngenes;
+                    const uint32_t bit = 1u << (c & 31);
+                    for (int64_t j = 0; j < w; j++) {
+                        const double x = col[row[j]];
+                        if (x > 0) mask[(b + j) * W + (c >> 5)] |= bit;
+                        else if (x == 0) nzero[b + j]++;
+                    }
+                }
+            } else {
+                for (int64_t j = 0; j < w; j++) {
+                    const double* r = v.X + row[j] * v.ncells;
+                    uint32_t* m = mask + (b + j) * W;
+                    int32_t nz = 0;
+                    for (int64_t c = 0; c < v.ncells; c++) {
+                        if (r[c] > 0) m[c >> 5] |= 1u << (c & 31);
+                        else if (r[c] == 0) nz++;
+                    }
+                    nzero[b + j] = nz;
+                }
+            }
+        }
+    });
 }
 
 // R/Cluster_actions.R:25  luOutlier: sum(table(class) >= min.size), per gene, optionally restricted to one condition

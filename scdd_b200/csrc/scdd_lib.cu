@@ -23,6 +23,7 @@
 
 #include "kernels.cuh"
 #include "fedp.cuh"
+#include "zeroes.cuh"
 #include "dense_host.h"
 
 using namespace scdd;
@@ -1435,6 +1436,121 @@ int32_t scdd_dense_cell_covariate(const double* X, int64_t ngenes, int64_t ncell
     if (!dense::cell_values_to_csr(v, cell_values, genes, nsel, gene_off, out))
         return fail(SCDD_ERR_BAD_ARG, "gene_off does not match the nonzero cells of the selected genes");
     return SCDD_OK;
+}
+
+void scdd_default_glm_opts(scdd_glm_opts* o) {
+    if (!o) return;
+    o->prior_scale = 2.5;
+    o->prior_scale_for_intercept = 10.0;
+    o->prior_df = 1.0;
+    o->epsilon = 1e-8;
+    o->maxit = 100;
+    o->reserved = 0;
+}
+
+// bayesglm's scaled = TRUE rule for one predictor column: 1 for a constant, max - min for a two-valued column,
+// 2 sd(x) (n - 1 denominator) otherwise
+static double predictor_scale(std::vector<double> x) {
+    if (x.empty()) return 1.0;
+    const size_t n = x.size();
+    double mean = 0;
+    for (double v : x) mean += v;
+    mean /= (double)n;
+    double ss = 0;
+    for (double v : x) ss += (v - mean) * (v - mean);
+    std::sort(x.begin(), x.end());
+    const size_t ncat = (size_t)(std::unique(x.begin(), x.end()) - x.begin());
+    if (ncat == 2) return x[1] - x[0];
+    if (ncat > 2) return 2.0 * std::sqrt(ss / (double)(n - 1));
+    return 1.0;
+}
+
+int32_t scdd_test_zeroes(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_level2,
+                         const int32_t* these, int64_t nthese, const scdd_glm_opts* opts, double* pvalue,
+                         double* detail, scdd_stats* stats) {
+    if (ngenes < 0 || ncells < 0 || nthese < 0 || nthese > INT32_MAX || ncells > INT32_MAX - 64 ||
+        (ngenes * ncells > 0 && (!X || !cell_level2)) || (nthese > 0 && !pvalue))
+        return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    if (!these && nthese > ngenes) return fail(SCDD_ERR_BAD_ARG, "nthese exceeds the number of rows");
+    if (these)
+        for (int64_t j = 0; j < nthese; j++)
+            if (these[j] < 0 || these[j] >= ngenes) return fail(SCDD_ERR_BAD_ARG, "row index out of range");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nthese == 0) return SCDD_OK;
+    scdd_glm_opts o;
+    scdd_default_glm_opts(&o);
+    if (opts) o = *opts;
+    if (!(o.prior_scale > 0) || !(o.prior_scale_for_intercept > 0) || !(o.prior_df > 0) || !(o.epsilon > 0) || o.maxit < 1)
+        return fail(SCDD_ERR_BAD_ARG, "bad glm options");
+    int64_t n2 = 0;
+    for (int64_t c = 0; c < ncells; c++) n2 += cell_level2[c] != 0;
+    if (n2 == 0 || n2 == ncells) return fail(SCDD_ERR_BAD_ARG, "factor(cond) needs two levels");
+    if (device_count_quiet() < 1) return fail(SCDD_ERR_NO_DEVICE, "no CUDA device available: libscdd_b200 has no CPU fallback");
+    return guarded([&]() -> int {
+        const int64_t W = (ncells + 31) / 32;
+        dense::View v{X, ngenes, ncells, col_major != 0};
+        std::vector<uint32_t> mask((size_t)nthese * W), lvl((size_t)W, 0u);
+        std::vector<int32_t> nzero((size_t)nthese);
+        std::vector<double> det((size_t)ncells);
+        dense::zero_mask(v, these, nthese, W, mask.data(), nzero.data(), det.data());
+        for (int64_t c = 0; c < ncells; c++)
+            if (cell_level2[c] != 0) lvl[c >> 5] |= 1u << (c & 31);
+        ZeroGlmArgs a{};
+        constexpr double MIN_PRIOR_SCALE = 1e-12;   // bayesglm's min.prior.scale
+        a.scale[0] = o.prior_scale_for_intercept;
+        a.scale[1] = std::max(o.prior_scale / predictor_scale(det), MIN_PRIOR_SCALE);
+        a.scale[2] = o.prior_scale;                 // the 0/1 dummy: max - min = 1
+        a.df = o.prior_df;
+        a.epsilon = o.epsilon;
+        a.maxit = o.maxit;
+        a.W = W;
+        a.ncells = (int)ncells;
+        a.ngenes = (int)nthese;
+        std::vector<int> devs = active_devices();
+        CK(cudaSetDevice(devs[0]));
+        cudaStream_t s;
+        CK(cudaStreamCreate(&s));
+        try {
+            DevBuf<uint32_t> d_mask, d_lvl;
+            DevBuf<int32_t> d_nz;
+            DevBuf<double> d_det, d_p, d_detail;
+            d_mask.alloc(mask.size()); d_lvl.alloc(lvl.size()); d_nz.alloc(nzero.size());
+            d_det.alloc(det.size()); d_p.alloc((size_t)nthese);
+            if (detail) d_detail.alloc((size_t)nthese * 8);
+            cudaEvent_t t0, t1;
+            CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+            CK(cudaMemcpyAsync(d_mask.p, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_lvl.p, lvl.data(), lvl.size() * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_nz.p, nzero.data(), nzero.size() * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_det.p, det.data(), det.size() * 8, cudaMemcpyHostToDevice, s));
+            a.mask = d_mask.p; a.lvl = d_lvl.p; a.det = d_det.p; a.nzero = d_nz.p;
+            a.pvalue = d_p.p; a.detail = detail ? d_detail.p : nullptr;
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, devs[0]));
+            const int threads = 128;   // 4 genes per CTA
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nthese + 3) / 4, (int64_t)prop.multiProcessorCount * 16));
+            CK(cudaEventRecord(t0, s));
+            zero_glm_kernel<<<grid, threads, 0, s>>>(a);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(t1, s));
+            CK(cudaMemcpyAsync(pvalue, d_p.p, (size_t)nthese * 8, cudaMemcpyDeviceToHost, s));
+            if (detail) CK(cudaMemcpyAsync(detail, d_detail.p, (size_t)nthese * 64, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (stats) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, t0, t1));
+                stats->total_ms = ms;
+                stats->h2d_bytes = (double)(mask.size() + lvl.size() + nzero.size()) * 4 + (double)det.size() * 8;
+                stats->d2h_bytes = (double)nthese * (detail ? 72 : 8);
+            }
+            cudaEventDestroy(t0); cudaEventDestroy(t1);
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        CK(cudaStreamDestroy(s));
+        return SCDD_OK;
+    });
 }
 
 int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, int32_t col_major, const int32_t* cell_cond01,

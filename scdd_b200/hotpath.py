@@ -92,6 +92,44 @@ def cell_covariate(normcounts, cell_values, gene_off, genes=None):
     return out
 
 
+def factor_level2(condition):
+    """1 where the cell is in the SECOND level of factor(cond) (levels = sort(unique(cond))): the dummy column of
+    model.matrix(~ factor(cond)) under treatment contrasts, R/classify.dd.R:268"""
+    cond = np.asarray(condition)
+    lev = sorted(set(cond.tolist()))
+    if len(lev) != 2:
+        raise ValueError("Error: Please specify valid condition labels.")
+    return np.ascontiguousarray(cond == lev[1], dtype=np.int32)
+
+
+def test_zeroes(normcounts, condition, these=None, epsilon=1e-8, maxit=100, detail=False):
+    """testZeroes, R/classify.dd.R:262-286: the Wald p-value of the condition coefficient of
+    arm::bayesglm(y > 0 ~ detection + factor(cond), binomial) for the rows `these` (0-based; default all), NaN for a
+    gene without zeros.  Returns (p, stats) or (p, detail[n, 8], stats); detail = coef[3], se[3], iterations, deviance."""
+    X = np.asarray(normcounts, dtype=np.float64)
+    col_major = X.flags.f_contiguous and not X.flags.c_contiguous
+    if not col_major:
+        X = np.ascontiguousarray(X)
+    ng, nc = X.shape
+    l2 = factor_level2(condition)
+    assert l2.size == nc
+    if these is not None:
+        these = np.ascontiguousarray(these, dtype=np.int32)
+    n = ng if these is None else these.size
+    o = _lib.GlmOpts()
+    _lib.lib().scdd_default_glm_opts(C.byref(o))
+    o.epsilon, o.maxit = float(epsilon), int(maxit)
+    p = np.empty(n, dtype=np.float64)
+    det = np.empty((n, 8), dtype=np.float64) if detail else None
+    st = Stats()
+    _lib.check(_lib.lib().scdd_test_zeroes(X.ctypes.data, ng, nc, int(col_major), l2.ctypes.data, _lib.ptr(these), n,
+                                           C.byref(o), p.ctypes.data, _lib.ptr(det), C.byref(st)))
+    return (p, det, st.as_dict()) if detail else (p, st.as_dict())
+
+
+test_zeroes.__test__ = False
+
+
 def labels_to_dense(normcounts, condition, labels, gene_off, genes=None, which=-1, ref=None):
     """Zhat matrix (R/scDD.R:528-552): 0 where the count is zero, the class label on the nonzero cells of the fitted
     genes, 1 elsewhere.  which = 0 / 1 keeps only that condition's columns."""

@@ -9,6 +9,7 @@
  */
 #ifndef MOCK_RINTERNALS_H
 #define MOCK_RINTERNALS_H
+#include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -33,6 +34,9 @@ extern SEXP R_NilValue;
 extern int R_NaInt;
 #define NA_INTEGER R_NaInt
 #define NA_LOGICAL R_NaInt
+extern double R_NaReal;                  /* R's NA_real_: a NaN whose low word is 1954 */
+#define NA_REAL R_NaReal
+#define ISNAN(x) (isnan(x) != 0)         /* R_ext/Arith.h */
 
 SEXP Rf_allocVector(unsigned int type, R_xlen_t n);
 SEXP Rf_allocMatrix(unsigned int type, int nrow, int ncol);

@@ -20,6 +20,13 @@ struct mock_sexp {
 static struct mock_sexp nil_obj = {NILSXP, 0, NULL, 0, 0, NULL};
 SEXP R_NilValue = &nil_obj;
 int R_NaInt = (-2147483647 - 1);
+double R_NaReal;
+
+__attribute__((constructor)) static void mock_init_na(void) {
+    union { double d; unsigned long long u; } x;
+    x.u = 0x7FF00000000007A2ULL;         /* arithmetic.c R_ValueOfNA: hw = 0x7FF00000, lw = 1954 */
+    R_NaReal = x.d;
+}
 
 static int protect_depth = 0, protect_max = 0, protect_underflow = 0;
 static long n_alloc = 0;

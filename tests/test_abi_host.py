@@ -44,7 +44,8 @@ def test_compute_fails_loudly_without_gpu():
     off = np.array([0, 20], dtype=np.int64)
     for call in (lambda: hp.fit_observed(y, c, off), lambda: hp.perm_bf(y, c, off, 2, seed6=hp.gene_seeds(1, 1)),
                  lambda: hp.ks(y, c, off),
-                 lambda: hp.fedp(y, c, off, np.ones(20, dtype=np.int32), np.ones(20, dtype=np.int32))):
+                 lambda: hp.fedp(y, c, off, np.ones(20, dtype=np.int32), np.ones(20, dtype=np.int32)),
+                 lambda: hp.test_zeroes(np.arange(40.0).reshape(2, 20) % 3, c)):
         with pytest.raises(hp.ScddError) as e:
             call()
         assert e.value.code == -1 and "no CPU fallback" in str(e.value)

@@ -209,6 +209,16 @@ def test_glue_on_gpu_matches_ctypes_binding(glue, golden_dir):
     fe = glue.call("C_scdd_fedp", glue.real(vals), glue.real(off), glue.int(c), glue.int(cls_oa), glue.int(cls_c), glue.nil, glue.int([3]))
     ps, pf, cnt, _ = hp.fedp(vals, c, off, cls_oa, cls_c)
     assert np.array_equal(glue.get(fe, "p.shift"), ps, equal_nan=True) and np.array_equal(glue.get(fe, "counts"), cnt.T)
+    # testZeroes: 1-based rows in, NA_real_ (payload 1954) for a gene without zeros
+    Xz = np.array(X, dtype=np.float64)
+    Xz[2] = np.abs(Xz[2]) + 1.0
+    these = np.array([1, 3, 20, 7])
+    tz = glue.call("C_scdd_test_zeroes", glue.matrix(Xz), glue.int([Xz.shape[0]]), glue.int([Xz.shape[1]]),
+                   glue.int(hp.factor_level2(cond)), glue.int(these))
+    pz, _ = hp.test_zeroes(Xz, cond, these=these - 1)
+    got = glue.value(tz)
+    assert np.array_equal(got, pz, equal_nan=True) and np.isnan(got[1])
+    assert got[1:2].view(np.uint64)[0] & 0xFFFFFFFF == 1954
     # Ctrl-C: R_CheckUserInterrupt() fires at the second poll; the library unwinds, THEN the glue raises the R error
     glue.L.mock_interrupt_after(1)
     with pytest.raises(RuntimeError, match="interrupted"):

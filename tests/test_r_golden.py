@@ -103,3 +103,25 @@ def test_permutations_against_r(name):
         s = po.lecuyer_next_substream(s)
     ref = po.perm_batch(logy, c01, off, B, seed6=seeds, cfg=po.make_cfg(**PRI))
     np.testing.assert_allclose(ref, np.array([p["bf_perm"] for p in g["perms"]]), rtol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["scDatExSim", "scDatEx"])
+def test_zero_test_against_arm(name):
+    """oracle/zeroes_oracle.py against arm::bayesglm itself: the pin the restatement lacks today"""
+    from oracle import zeroes_oracle as zo
+    g = _load(f"r_golden_{name}.json")
+    if "zero_p" not in g:
+        pytest.skip("golden file predates the testZeroes dump")
+    d = np.load(os.path.join(GOLD, f"{name}.npz"), allow_pickle=True)
+    X, cond = d["normcounts"], d["condition"]
+    p, det = zo.test_zeroes(X, cond, detail=True)
+    want = np.array([np.nan if v is None else v for v in g["zero_p"]])
+    assert np.array_equal(np.isnan(p), np.isnan(want))
+    np.testing.assert_allclose(p[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-8)
+    for r, z in zip(det, g["zero_fits"]):
+        if z["na"] == "true":
+            assert r is None
+            continue
+        np.testing.assert_allclose(r["coef"], z["coef"], rtol=1e-8)
+        np.testing.assert_allclose(r["se"], z["se"], rtol=1e-8)
+        assert r["iter"] == int(z["iter"][0])

@@ -16,6 +16,8 @@
 #   * permutation numerators of scDD:::permMclustGene under bplapply(SerialParam(RNGseed = 816)), B permutations,
 #     and the permutations themselves (sample(1:n) per stream)                                        (R/permutations.R:211-286)
 #   * ks.test(x1, x2, exact = FALSE): statistic and p.value on the nonzero raw values                 (R/Test_KS.R:56-65)
+#   * scDD:::testZeroes over all rows, and per gene the arm::bayesglm fit behind it: coefficients, standard errors,
+#     iterations, deviance, prior.scale, prior.sd                                                      (R/classify.dd.R:262-286)
 # and once: versions, RNG known answers (Mersenne-Twister and L'Ecuyer-CMRG sample()/runif, nextRNGStream,
 # nextRNGSubStream, the .Random.seed BiocParallel hands to bplapply elements 1..4 for RNGseed = 7).
 suppressPackageStartupMessages({
@@ -81,7 +83,19 @@ dump_one <- function(name, sce) {
     list(seed = seed0, bf = bf, first = first)
   }, BPPARAM = SerialParam(RNGseed = 816))
   perms <- lapply(perm, function(p) obj(random_seed = int(p$seed), bf_perm = num(p$bf), first_perm = int(p$first)))
-  json <- obj(name = str(name), B = B, RNGseed = 816, genes = arr(genes), perms = arr(perms))
+  # testZeroes: the p-values the package returns, and the bayesglm objects behind them (all rows count in `detection`)
+  pz <- scDD:::testZeroes(X, cond)
+  detection <- colSums(X > 0) / nrow(X)
+  zfits <- lapply(seq_len(ng), function(g) {
+    y <- X[g, ]
+    if (sum(y == 0) == 0) return(obj(na = "true"))
+    M1 <- suppressWarnings(arm::bayesglm(y > 0 ~ detection + factor(cond), family = binomial(link = "logit"), Warning = FALSE))
+    cf <- summary(M1)$coefficients
+    obj(na = "false", coef = num(cf[, 1]), se = num(cf[, 2]), p = num(cf[, 4]), iter = num(M1$iter), deviance = num(M1$deviance),
+        prior_scale = num(M1$prior.scale), prior_sd = num(M1$prior.sd), converged = str(as.character(M1$converged)))
+  })
+  json <- obj(name = str(name), B = B, RNGseed = 816, genes = arr(genes), perms = arr(perms),
+              zero_p = num(pz), zero_fits = arr(zfits), arm = str(as.character(packageVersion("arm"))))
   writeLines(json, file.path(outdir, paste0("r_golden_", name, ".json")))
   message("wrote ", name, ": ", ng, " genes")
 }
