@@ -302,6 +302,14 @@ __device__ __forceinline__ void estep_points(const double (&x)[U], const P& prm,
     for (int i = 0; i < N; i++) p[i] = __dsub_rn(t[i], MAGIC);                             // term_r
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = fma(p[i], prm.c(1), a[i]);
+    if (SAT) {
+        // a saturated term is below every finite one by construction (k = KMIN), but beyond |a| ~ 2^52 ln2 / 2^11 =
+        // 1.5e12 the sum a c + MAGIC is no longer an integer and the "reduced argument" is garbage of any size: with
+        // 1 + s <= 1/4 the exponent insert below would borrow from the sign bit.  Reachable when a variance sits
+        // between eps and ~1e-11 (range^2 / 2 sigsq > 1.5e12): values that almost, but not exactly, coincide.
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = (n[i] == NSAT) ? 0.0 : r[i];
+    }
 #pragma unroll
     for (int i = 0; i < N; i++) p[i] = fma(prm.c(2), r[i], 0.5);                   // term_s
 #pragma unroll

@@ -365,3 +365,37 @@ def test_mid_size_bulk_fit_sets_on_four_warp_teams():
     assert st["fit_sets"] == 1200 and st["failed_sets"] == 0
     np.testing.assert_allclose(terms, ref["jp_terms"], rtol=RTOL)
     np.testing.assert_allclose(out, ref["bf_perm"], rtol=RTOL)
+
+
+def test_almost_coincident_values_keep_tiny_variances():
+    """A cluster of values that almost, but not exactly, coincide (spread 3e-7) far from the rest: mclust keeps valid
+    components with variances ~1e-13 (> eps), whose log-terms for the other points reach -5e13 -- beyond the range in
+    which the kernel's integer extraction is meaningful; such terms must count as exact zeros (mclust.f: below -708)."""
+    rng = np.random.default_rng(3)
+    rows, conds = [], []
+    for trial in range(6):
+        n = 60 + 10 * trial
+        v = rng.normal(1.0, 0.8, size=n)
+        k = 12 + trial
+        v[:k] = 4.0 + rng.normal(0, 3e-7, size=k)
+        rows.append(v)
+        conds.append((rng.random(n) < 0.5).astype(np.int32))
+    off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.int64)
+    logy, c01 = np.concatenate(rows), np.concatenate(conds)
+    fits, cls_oa, cls_c, bf, den, st = hp.fit_observed(logy, c01, off, cfg=hp.make_cfg(**PRIORS), allow_failed=True)
+    ofits, ocls_oa, ocls_c, obf, oden = po.genefit_batch(logy, c01, off, cfg=po.make_cfg(**PRIORS))
+    for g in range(off.size - 1):
+        for w in range(3):
+            assert fits[g, w]["G"] == ofits[g][w]["G"], (g, w)
+            np.testing.assert_allclose(fits[g, w]["bic"], ofits[g][w]["bic"], rtol=1e-7)
+    # the regime is really exercised: most G >= 2 rows of the tables hold a variance below 1e-11
+    tiny = sum(int(r["valid"] and np.min(r["sigsq"]) < 1e-11) for v in rows for r in po.fit_table(v, po.make_cfg(**PRIORS))[1:])
+    assert tiny >= 12
+    assert np.array_equal(cls_oa, ocls_oa) and np.array_equal(cls_c, ocls_c)
+    np.testing.assert_allclose(bf, obf, rtol=1e-7)
+    np.testing.assert_allclose(den, oden, rtol=1e-7)
+    B = 8
+    seeds = hp.gene_seeds(11, off.size - 1)
+    out, st2 = hp.perm_bf(logy, c01, off, B, seed6=seeds, cfg=hp.make_cfg(**PRIORS), allow_failed=True)
+    ref = po.perm_batch_ex(logy, c01, off, B, seed6=seeds, cfg=po.make_cfg(**PRIORS))
+    np.testing.assert_allclose(out, ref["bf_perm"], rtol=1e-7, equal_nan=True)
