@@ -296,6 +296,7 @@ def run_full(args):
                           "perm_call_device_ms": st["total_ms"], "fit_kernel_ms": st["fit_kernel_ms"],
                           "rng_kernel_ms": st["rng_kernel_ms"], "observed_ms": meta["stats"]["observed"]["fit_kernel_ms"],
                           "fedp_ms": meta["stats"].get("feDP", {}).get("total_ms"),
+                          "host_phases_s": {k: round(v, 4) for k, v in meta["stats"].get("host_phases_s", {}).items()},
                           "genes_fitted": int(meta["tofit"].size), "const_sets": st["const_sets"], "failed_sets": st["failed_sets"],
                           "n_significant": int((np.asarray(G["nonzero.pvalue.adj"]) < 0.05).sum()),
                           "pvalue_checksum": float(np.nansum(p)),

@@ -206,6 +206,32 @@ int32_t scdd_labels_to_dense(const double* X, int64_t ngenes, int64_t ncells, in
 int32_t scdd_cluster_counts(const int32_t* labels, const int32_t* cond01, const int64_t* gene_off, int32_t ngenes,
                             int32_t min_size, int32_t which, int32_t* counts);
 
+/* ---- classifyDD, R/classify.dd.R:86-238 ----
+ * The DE / DP / DM / DB / NC pattern of the genes `genes[nsel]` (0-based indices into the block) from the three
+ * clusterings of scdd_fit_observed (cls_oa, cls_c): label compression (:124-158), luOutlier / findOutliers
+ * (R/Cluster_actions.R:25,78), the normal-gamma posterior of every cluster (getPosteriorParams, :19-37), the
+ * Monte-Carlo comparison of every (cluster of condition 1, cluster of condition 2) pair (:165-187: 10,000 Student-t
+ * draws each, "different" iff all sampled differences share a sign) and the decision tree (:189-234).  p_shift[ngenes]
+ * (nullable) = the unadjusted mean-shift p-values of scdd_fedp, used by the multimodal-DE rule (:206-214).
+ * The draws run on the device, one warp per comparison, from Philox streams keyed by (seed, comparison index): the
+ * reference's distribution, NOT R's stream (classifyDD consumes the user's RNG; see csrc/classify.cuh).
+ * opts->comp_off [nsel+1] / comp_detail [comp_cap*9] (nullable) return the comparisons: df1, scale1, m1, df2, scale2,
+ * m2, flag, min, max of the sampled differences (at most 25 comparisons per gene). */
+enum { SCDD_CAT_NC = 0, SCDD_CAT_DE = 1, SCDD_CAT_DP = 2, SCDD_CAT_DM = 3, SCDD_CAT_DB = 4 };
+typedef struct {
+    int32_t ndraws;          /* 10000 */
+    int32_t reserved;
+    uint64_t seed;
+    int64_t* comp_off;
+    double* comp_detail;
+    int64_t comp_cap;
+} scdd_classify_opts;
+void scdd_default_classify_opts(scdd_classify_opts* opts);
+int32_t scdd_classify(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                      const int32_t* cls_oa, const int32_t* cls_c, const int32_t* genes, int32_t nsel,
+                      const double* p_shift, const scdd_cfg* cfg, const scdd_classify_opts* opts,
+                      int32_t* category, scdd_stats* stats);
+
 /* ---- testZeroes, R/classify.dd.R:262-286 ----
  * Per gene with at least one zero: arm::bayesglm(y > 0 ~ detection + factor(cond), binomial(logit)) and the Wald
  * p-value of the condition coefficient, summary(M1)$coefficients[3, 4]; NaN (R's NA) for a gene without zeros (:267).
@@ -261,6 +287,8 @@ int32_t scdd_selftest_softmax(const double* a, int32_t G, double* z, double* log
 int32_t scdd_selftest_log(const double* x, int32_t n, double* out);
 /* the host-side tail of scdd_fedp: out[i] = 2 * pt(-|t[i]|, df[i]) */
 int32_t scdd_selftest_student_p(const double* t, const double* df, int32_t n, double* out);
+/* the device's Student-t generator behind scdd_classify (needs a GPU): out[i] = one t_df variate of stream i */
+int32_t scdd_selftest_student_t(double df, int32_t n, uint64_t seed, double* out);
 /* measured fp64 FMA throughput of the device (TFLOP/s, DFMA = 2 flop), used as the roofline denominator */
 double scdd_measure_fp64_peak(int32_t device, double* sm_clock_mhz_out);
 

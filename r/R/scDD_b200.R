@@ -1,8 +1,9 @@
 # scDD_b200.R -- drop-in dispatcher: scDD() with the reference's exact signature, argument checks, messages and result
 # objects (R/scDD.R:217-602), with the per-gene work of the hot path done by libscdd_b200.so through the helpers of
 # scDD_gpu.R.  A maintainer replaces the body of R/scDD.R by this file (or sources it after the package) -- nothing
-# else of the package changes: classifyDD() and results() are the reference's own; testKS() and testZeroes() are
-# redefined at the end of this file with the reference's signatures.
+# else of the package changes: results() is the reference's own, classifyDD() too when options(scdd_b200.classify = "R")
+# (default: the library's, see classifyDD_gpu); testKS() and testZeroes() are redefined at the end of this file with the
+# reference's signatures.
 #
 # Written from the reference's behaviour, not from its text: the three bplapply fan-outs and the per-gene R loops are
 # gone, so the function is organised around flat vectors (one CSR block for all fitted genes) instead of lists.
@@ -101,20 +102,27 @@ scDD <- function(SCdat,
   cats.all <- pvals.all <- rep(NA, nrow(X))
   pvals.all[tofit] <- pvals
 
-  ## ---- categories: classifyDD stays the reference's R (it draws from the user's RNG stream), feDP's loop is a kernel ----
+  ## ---- categories: feDP's per-gene loop and classifyDD's Monte-Carlo comparisons are kernels ----
   if (categorize) {
     message("Classifying significant genes into patterns")
-    dd.cats <- classifyDD(Xf, cond, sig, oa, c1, c2, alpha = prior[1], m0 = prior[2], s0 = prior[3], a0 = prior[4],
-                          b0 = prior[5], log.nonzero = TRUE, ref = ref, min.size = min.size)
-    cats <- rep("NS", ng)
-    cats[sig] <- dd.cats
     cdr <- if (adjust.perms) cell_covariate_gpu(Xf, C, fit$csr$off) else NULL
-    extraDP <- feDP_gpu(fit$csr, fit$raw, sig, ng, cdr = cdr, testZeroes = testZeroes, min.size = min.size)
+    fe <- fedp_stats_gpu(fit$csr, fit$raw, cdr, min.size)            # p.shift / p.fisher / counts of every gene, once
+    on.device <- getOption("scdd_b200.classify", "gpu") == "gpu"
+    cseed <- if (is.null(RNGseed)) 1L else as.integer(RNGseed)
+    classify <- function(these, k) {
+      if (on.device) {
+        classifyDD_gpu(fit$csr, fit$raw, these, prior, min.size, fe$p.shift, seed = cseed + k)
+      } else {
+        classifyDD(Xf, cond, these, oa, c1, c2, alpha = prior[1], m0 = prior[2], s0 = prior[3], a0 = prior[4],
+                   b0 = prior[5], log.nonzero = TRUE, ref = ref, min.size = min.size)
+      }
+    }
+    cats <- rep("NS", ng)
+    cats[sig] <- classify(sig, 0L)
+    extraDP <- feDP_gpu(fit$csr, fit$raw, sig, ng, cdr = cdr, testZeroes = testZeroes, min.size = min.size, stats = fe)
     cats[-sig] <- names(extraDP)
     NCs <- which(p.adjust(pvals, method = "BH") > (if (testZeroes) level / 2 else level) & cats == "NC")
-    NC.cats <- classifyDD(Xf, cond, NCs, oa, c1, c2, alpha = prior[1], m0 = prior[2], s0 = prior[3], a0 = prior[4],
-                          b0 = prior[5], log.nonzero = TRUE, ref = ref, min.size = min.size)
-    cats[NCs] <- NC.cats
+    cats[NCs] <- classify(NCs, 1L)
     cats.all[tofit] <- cats
   }
 

@@ -107,13 +107,18 @@ testKS_gpu <- function(dat, condition, inclZero = TRUE) {
   .Call(C_scdd_ks, g$vals, g$off, g$cond01)$p
 }
 
+# the per-gene pieces of feDP for every gene of the block in one call: p.shift (Welch t / lm coefficient), p.fisher,
+# counts (luOutlier of oa / c1 / c2).  classifyDD_gpu() needs p.shift too, so scDD() computes this once.
+fedp_stats_gpu <- function(g, fit, cdr = NULL, min.size = 3)
+  .Call(C_scdd_fedp, g$vals, g$off, g$cond01, as.integer(fit$class.oa), as.integer(fit$class.c),
+        if (is.null(cdr)) NULL else as.double(cdr), as.integer(min.size))
+
 # replaces feDP(), R/classify.dd.R:314-383: the per-gene loop runs on the device, the labelling (:377-382) stays R.
 # g: the .gene_csr() list of pe_mat; fit: the list C_scdd_fit_observed returned (class.oa, class.c); cdr: the cellular
-# detection rate of every nonzero cell in CSR order when adjust.perms (else NULL).
-feDP_gpu <- function(g, fit, sig_genes, nrow_pe, cdr = NULL, testZeroes = FALSE, min.size = 3) {
+# detection rate of every nonzero cell in CSR order when adjust.perms (else NULL); stats: fedp_stats_gpu() if at hand.
+feDP_gpu <- function(g, fit, sig_genes, nrow_pe, cdr = NULL, testZeroes = FALSE, min.size = 3, stats = NULL) {
   pval.thresh <- if (testZeroes) 0.025 else 0.05
-  r <- .Call(C_scdd_fedp, g$vals, g$off, g$cond01, as.integer(fit$class.oa), as.integer(fit$class.c),
-             if (is.null(cdr)) NULL else as.double(cdr), as.integer(min.size))
+  r <- if (is.null(stats)) fedp_stats_gpu(g, fit, cdr, min.size) else stats
   ns_genes <- (1:nrow_pe)[-sig_genes]              # R quirk kept: empty when there is no significant gene
   cnt <- r$counts[, ns_genes, drop = FALSE]
   cat <- ifelse(!is.na(r$p.fisher[ns_genes]) & r$p.fisher[ns_genes] < 0.05, "DP", "NS")
@@ -122,6 +127,18 @@ feDP_gpu <- function(g, fit, sig_genes, nrow_pe, cdr = NULL, testZeroes = FALSE,
   cat[pval.ns < pval.thresh & cnt[2, ] == cnt[3, ] & cnt[2, ] == cnt[1, ] & cnt[2, ] > 1] <- "DP"
   names(pval.ns) <- cat
   pval.ns
+}
+
+# replaces classifyDD(), R/classify.dd.R:86-238, for the genes `these` (1-based) of the fitted block: the label
+# bookkeeping and the posterior parameters run on host threads of the library, the 10,000-draw Monte-Carlo comparison
+# of every pair of cluster means (:165-187) on the device.  The draws come from Philox streams keyed by `seed`, not from
+# R's RNG: same distribution, another stream (the reference's own classifyDD consumes .Random.seed); set
+# options(scdd_b200.classify = "R") to keep the reference's function instead.
+classifyDD_gpu <- function(g, fit, these, prior, min.size, p.shift, seed = 1L) {
+  if (length(these) == 0) return(character(0))
+  code <- .Call(C_scdd_classify, g$vals, g$off, g$cond01, as.integer(fit$class.oa), as.integer(fit$class.c),
+                as.integer(these), as.double(p.shift), as.double(prior), as.integer(min.size), as.integer(seed))
+  c("NC", "DE", "DP", "DM", "DB")[code + 1L]
 }
 
 # replaces the bplapply of arm::bayesglm fits inside testZeroes, R/classify.dd.R:262-286.  factor(cond) sorts its

@@ -188,6 +188,33 @@ SEXP C_scdd_cell_covariate(SEXP dat, SEXP nrow, SEXP ncol, SEXP values, SEXP off
     return out;
 }
 
+/* classifyDD, R/classify.dd.R:86-238, for the genes `genes` (1-based) of the block: integer codes 0..4 =
+ * NC, DE, DP, DM, DB.  p_shift: the unadjusted mean-shift p-values of C_scdd_fedp (all genes) or NULL. */
+SEXP C_scdd_classify(SEXP vals, SEXP off, SEXP cond01, SEXP cls_oa, SEXP cls_c, SEXP genes, SEXP p_shift, SEXP prior,
+                     SEXP min_size, SEXP seed) {
+    int ng;
+    need_type(vals, REALSXP, "vals"); need_type(cond01, INTSXP, "cond01"); need_type(cls_oa, INTSXP, "class.oa");
+    need_type(cls_c, INTSXP, "class.c"); need_type(genes, INTSXP, "genes");
+    if (p_shift != R_NilValue) need_type(p_shift, REALSXP, "p.shift");
+    int64_t *o = offsets(off, &ng);
+    if (XLENGTH(vals) != (R_xlen_t)o[ng] || XLENGTH(cond01) != XLENGTH(vals) || XLENGTH(cls_oa) != XLENGTH(vals) ||
+        XLENGTH(cls_c) != XLENGTH(vals) || (p_shift != R_NilValue && LENGTH(p_shift) != ng))
+        Rf_error("scdd_b200: vals, cond01, class.oa, class.c must have off[ngenes+1] entries, p.shift one per gene");
+    scdd_cfg cfg = cfg_from(prior, min_size);
+    scdd_classify_opts op;
+    scdd_default_classify_opts(&op);
+    op.seed = (uint64_t)(unsigned int)asInteger(seed);
+    int n = LENGTH(genes);
+    int32_t *rows = (int32_t *)R_alloc(n > 0 ? n : 1, sizeof(int32_t));
+    for (int j = 0; j < n; j++) rows[j] = INTEGER(genes)[j] - 1;
+    SEXP out = PROTECT(allocVector(INTSXP, n));
+    int rc = scdd_classify(REAL(vals), o, INTEGER(cond01), ng, INTEGER(cls_oa), INTEGER(cls_c), rows, n,
+                           p_shift == R_NilValue ? NULL : REAL(p_shift), &cfg, &op, INTEGER(out), NULL);
+    if (rc != SCDD_OK) { UNPROTECT(1); Rf_error("scdd_b200: %s", scdd_last_error()); }
+    UNPROTECT(1);
+    return out;
+}
+
 /* testZeroes, R/classify.dd.R:262-286: per row of `these` (1-based) the Wald p-value of the condition coefficient of
  * arm::bayesglm(y > 0 ~ detection + factor(cond), binomial); level2 = as.integer(factor(cond)) - 1L; NA for a gene
  * without zeros.  One kernel for all genes instead of a bplapply of bayesglm calls. */
@@ -295,6 +322,7 @@ static const R_CallMethodDef calls[] = {
     {"C_scdd_cluster_counts", (DL_FUNC)&C_scdd_cluster_counts, 5},
     {"C_scdd_fedp", (DL_FUNC)&C_scdd_fedp, 7},
     {"C_scdd_test_zeroes", (DL_FUNC)&C_scdd_test_zeroes, 5},
+    {"C_scdd_classify", (DL_FUNC)&C_scdd_classify, 10},
     {"C_scdd_device_count", (DL_FUNC)&C_scdd_device_count, 0},
     {NULL, NULL, 0}};
 

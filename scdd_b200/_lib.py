@@ -68,12 +68,22 @@ class GlmOpts(C.Structure):
                 ("epsilon", C.c_double), ("maxit", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ClassifyOpts(C.Structure):
+    """scdd_classify_opts of include/scdd_b200.h"""
+    _fields_ = [("ndraws", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("comp_off", C.c_void_p),
+                ("comp_detail", C.c_void_p), ("comp_cap", C.c_int64)]
+
+
+CATEGORIES = ("NC", "DE", "DP", "DM", "DB")      # SCDD_CAT_*
+
+
 EXPORTS = ["scdd_abi_version", "scdd_last_error", "scdd_device_count", "scdd_set_devices", "scdd_default_cfg",
            "scdd_fit_observed", "scdd_perm_bf", "scdd_perm_bf_ex", "scdd_release_cache", "scdd_ks", "scdd_rng_gene_seeds", "scdd_rng_sample_perms",
            "scdd_rng_mt_sample_perms", "scdd_plan_create", "scdd_plan_run_chunk", "scdd_plan_bf_device_ptr",
            "scdd_plan_stats", "scdd_plan_gene_costs", "scdd_plan_destroy", "scdd_selftest_x87_cumsum", "scdd_selftest_exp", "scdd_selftest_softmax", "scdd_selftest_log",
            "scdd_measure_fp64_peak", "scdd_dense_scan", "scdd_dense_to_csr", "scdd_dense_cell_covariate", "scdd_labels_to_dense", "scdd_cluster_counts", "scdd_fedp", "scdd_selftest_student_p",
-           "scdd_default_glm_opts", "scdd_test_zeroes"]
+           "scdd_default_glm_opts", "scdd_test_zeroes", "scdd_default_classify_opts", "scdd_classify",
+           "scdd_selftest_student_t"]
 
 
 def lib_path():
@@ -127,6 +137,11 @@ def lib():
     L.scdd_cluster_counts.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.scdd_fedp.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(Stats)]
     L.scdd_selftest_student_p.argtypes = [vp, vp, C.c_int32, vp]
+    L.scdd_default_classify_opts.argtypes = [C.POINTER(ClassifyOpts)]
+    L.scdd_default_classify_opts.restype = None
+    L.scdd_classify.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.POINTER(Cfg), C.POINTER(ClassifyOpts), vp,
+                                C.POINTER(Stats)]
+    L.scdd_selftest_student_t.argtypes = [C.c_double, C.c_int32, C.c_uint64, vp]
     L.scdd_default_glm_opts.argtypes = [C.POINTER(GlmOpts)]
     L.scdd_default_glm_opts.restype = None
     L.scdd_test_zeroes.argtypes = [vp, i64, i64, C.c_int32, vp, vp, i64, C.POINTER(GlmOpts), vp, vp, C.POINTER(Stats)]

@@ -152,88 +152,26 @@ def feDP(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, testZeroes=False, cdr
     return ns, pv, cat
 
 
-def _compress_labels(cls):
-    """R/classify.dd.R:124-158: when the label set has a gap (length(unique) != max) the labels above the FIRST missing
-    one move down by one (the reference handles one gap; so does this)."""
-    cls = np.asarray(cls).copy()
-    mx = int(cls.max())
-    present = np.unique(cls)
-    if present.size != mx:
-        missing = int(np.setdiff1d(np.arange(1, mx + 1), present)[0])
-        cls[cls > missing] -= 1
-    return cls
-
-
-def _posterior_params(y, cls, m0, s0, a0, b0):
-    """getPosteriorParams, R/classify.dd.R:19-37: per cluster k = 1..r the normal-gamma posterior (mk, sk, ak, bk)"""
-    r = np.unique(cls).size
-    nk = np.array([(cls == k).sum() for k in range(1, r + 1)], dtype=np.float64)
-    sy = np.array([y[cls == k].sum() for k in range(1, r + 1)])
-    syy = np.array([(y[cls == k] ** 2).sum() for k in range(1, r + 1)])
-    sk = s0 + nk
-    mk = (s0 * m0 + sy) / sk
-    ak = a0 + nk
-    bk = b0 + syy + s0 * m0 ** 2 - sk * mk ** 2
-    return mk, sk, ak, bk
-
-
-def _find_outliers(cls, min_size):
-    """findOutliers, R/Cluster_actions.R:78: labels of the clusters with at least min.size members"""
-    lab, cnt = np.unique(cls, return_counts=True)
-    return lab[cnt >= min_size].astype(int)
-
-
 def classifyDD(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, prior_param, adjust_perms=False, cdr=None, min_size=3,
-               rng=None, p_shift=None):
+               seed=1, p_shift=None):
     """classifyDD, R/classify.dd.R:86-238, over the CSR gene block: the DE / DP / DM / DB / NC pattern of each gene in
-    sig_genes (0-based) from the three clusterings.
+    sig_genes (0-based) from the three clusterings -- one library call (scdd_classify): label bookkeeping and posterior
+    parameters on host threads, the Monte-Carlo comparison of cluster means on the device.
 
-    The reference decides whether two cluster means differ by a Monte-Carlo draw: 10,000 Student-t variates per
-    cluster from R's own RNG stream (`rt`, :170-187), "different" iff all 10,000 sampled differences share a sign.  The
-    SAME test is made here with numpy's generator: the draws have the reference's distribution but not R's stream, so
-    a gene whose clusters sit right at the threshold can be labelled differently -- exactly as between two R runs with
-    different seeds.  (R's rt needs norm_rand / rgamma bit for bit, whose sources are not available offline; with the
-    R shim the reference's own classifyDD runs instead.)
-    p_shift: the unadjusted mean-shift p-values of scdd_fedp (Welch t / lm coefficient), used at :209-214."""
-    rng = np.random.default_rng(0) if rng is None else rng
-    m0, s0, a0, b0 = prior_param["mu0"], prior_param["s0"], prior_param["a0"], prior_param["b0"]
-    out = []
-    for g in np.asarray(sig_genes, dtype=np.int64):
-        o, e = int(gene_off[g]), int(gene_off[g + 1])
-        y, c = logy[o:e], cond01[o:e]
-        oa = _compress_labels(cls_oa[o:e])
-        c1 = _compress_labels(cls_c[o:e][c == 0])
-        c2 = _compress_labels(cls_c[o:e][c == 1])
-        n_oa, n_c1, n_c2 = luOutlier(oa, min_size), luOutlier(c1, min_size), luOutlier(c2, min_size)
-        mk1, sk1, ak1, bk1 = _posterior_params(y[c == 0], c1, m0, s0, a0, b0)
-        mk2, sk2, ak2, bk2 = _posterior_params(y[c == 1], c2, m0, s0, a0, b0)
-        comparisons = []
-        for a in _find_outliers(c1, min_size):
-            for b in _find_outliers(c2, min_size):
-                d = (rng.standard_t(round(ak1[a - 1]), 10000) * np.sqrt(bk1[a - 1] / (ak1[a - 1] * sk1[a - 1])) + mk1[a - 1]
-                     - rng.standard_t(round(ak2[b - 1]), 10000) * np.sqrt(bk2[b - 1] / (ak2[b - 1] * sk2[b - 1])) - mk2[b - 1])
-                comparisons.append(1 if (d.min() > 0 or d.max() < 0) else 0)
-        tot = sum(comparisons)
-        if n_c1 == n_c2:
-            if n_c1 == 1:
-                cat = "DE" if tot > 0 else "NC"
-            elif n_oa == n_c1:
-                cat = "DP" if tot <= n_c1 else "NC"
-            elif n_oa > n_c1:
-                if tot > n_c1 * (n_c1 - 1):
-                    # multimodal DE: an overall mean shift as well (t.test / lm coefficient, :206-214)
-                    ps = p_shift[g] if p_shift is not None else hp.fedp(logy[o:e], c, np.array([0, e - o]), cls_oa[o:e],
-                                                                        cls_c[o:e], cdr=None if cdr is None else cdr[o:e],
-                                                                        min_size=min_size)[0][0]
-                    cat = "DE" if ps < 0.01 else "NC"
-                else:
-                    cat = "NC"
-            else:
-                cat = "NC"
-        else:
-            cat = "DB" if tot == len(comparisons) else "DM"
-        out.append(cat)
-    return np.array(out, dtype=object)
+    The reference decides whether two cluster means differ by 10,000 Student-t draws per cluster from R's own RNG
+    stream (`rt`, :170-187), "different" iff all sampled differences share a sign.  The SAME test is made on the device
+    from Philox streams keyed by (seed, comparison): the reference's distribution, not R's stream, so a gene whose
+    clusters sit right at the threshold can be labelled differently -- exactly as between two R runs with different
+    seeds.  p_shift: the unadjusted mean-shift p-values of scdd_fedp (Welch t / lm coefficient), used at :206-214;
+    computed here when not given."""
+    sig_genes = np.asarray(sig_genes, dtype=np.int64)
+    if sig_genes.size == 0:
+        return np.zeros(0, dtype=object)
+    if p_shift is None:
+        p_shift = hp.fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=cdr if adjust_perms else None, min_size=min_size)[0]
+    cfg = hp.make_cfg(alpha=prior_param.get("alpha", 0.1), mu0=prior_param["mu0"], s0=prior_param["s0"],
+                      a0=prior_param["a0"], b0=prior_param["b0"], min_size=min_size)
+    return hp.classify(logy, cond01, gene_off, sig_genes, cls_oa, cls_c, p_shift=p_shift, cfg=cfg, seed=seed)[0]
 
 
 def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=False, param=None,
@@ -245,10 +183,18 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
                  per-gene L'Ecuyer-CMRG streams exactly as bplapply would.
     perm_source: "device" draws the permutations on the GPU (bit-exact R sampler); "host" draws them with the
                  library's host implementation of the same sampler and ships the indices (configs 1-2).
-    classify:    True runs classifyDD (DE / DP / DM / DB / NC labels; Monte-Carlo with numpy's generator -- see
-                 classifyDD); False leaves None for the genes the reference hands to classifyDD.
+    classify:    True runs classifyDD (DE / DP / DM / DB / NC labels; Monte-Carlo on the device -- see classifyDD);
+                 False leaves None for the genes the reference hands to classifyDD.
     """
     msg = (lambda s: print(s)) if verbose else (lambda s: None)
+    import time as _time
+    phases = {}
+    _t = [_time.perf_counter()]
+
+    def lap(name):                     # host wall time of the phase that just ended (seconds)
+        now = _time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + now - _t[0]
+        _t[0] = now
     if prior_param is None:
         prior_param = dict(alpha=0.10, mu0=0, s0=0.01, a0=0.01, b0=0.01)
     if not isinstance(SCdat, SingleCellExperiment):
@@ -295,7 +241,9 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
                       b0=prior_param["b0"], min_size=min_size)
     nf = tofit.size
     sel = None if nf == ngenes else tofit
+    lap("filters")
     logy, c01, off = hp.gene_csr(X, cond, ref=ref, genes=sel, nnz=(nnz0 + nnz1)[tofit])
+    lap("gene_csr")
     stats = {}
     if categorize:
         msg("Clustering observed expression data for each gene")
@@ -314,6 +262,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         # per-cell detection rate over the fitted genes (R/scDD.R:457, R/classify.dd.R:331), spread over the nonzero cells
         C = ((X if sel is None else X[tofit]) > 0).sum(axis=0) / float(nf)
         cdr = hp.cell_covariate(X, C, off, genes=sel)
+    lap("observed_fits")
     if permutations == 0:
         msg("Notice: Number of permutations is set to zero; using Kolmogorov-Smirnov to test for differences "
             "in distributions instead of the Bayes Factor permutation test")
@@ -352,6 +301,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         pvals = np.where(np.isnan(bf_perm).any(axis=1) | np.isnan(obs), np.nan, pvals)   # R: sum() over an NA is NA
         with np.errstate(invalid="ignore"):
             sig = np.nonzero(p_adjust_BH(pvals) < cut)[0]
+    lap("test")
     pvals_all = np.full(ngenes, np.nan)
     pvals_all[tofit] = pvals
     cats_all = [None] * ngenes
@@ -365,10 +315,11 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         fe_all = hp.fedp(logy, c01, off, cls_oa, cls_c, cdr=cdr if adjust_perms else None, min_size=min_size) \
             if nf else (np.zeros(0), np.zeros(0), np.zeros((0, 3), dtype=np.int32), {})
         p_shift_all = fe_all[0]
-        crng = np.random.default_rng(int(param.get("classify_seed", param.get("RNGseed", 1))))
+        lap("feDP_kernels")
+        cseed = int(param.get("classify_seed", param.get("RNGseed", 1)))
         if classify:
             cats[sig] = classifyDD(logy, c01, off, sig, cls_oa, cls_c, prior_param, adjust_perms=adjust_perms,
-                                   cdr=cdr if adjust_perms else None, min_size=min_size, rng=crng, p_shift=p_shift_all)
+                                   cdr=cdr if adjust_perms else None, min_size=min_size, seed=cseed, p_shift=p_shift_all)
         else:
             cats[sig] = None
         ns, _, cat_ns = feDP(logy, c01, off, sig, cls_oa, cls_c, testZeroes=testZeroes, cdr=cdr if adjust_perms else None,
@@ -379,11 +330,12 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         if classify:
             cats[to_classify] = classifyDD(logy, c01, off, to_classify, cls_oa, cls_c, prior_param,
                                            adjust_perms=adjust_perms, cdr=cdr if adjust_perms else None,
-                                           min_size=min_size, rng=crng, p_shift=p_shift_all)
+                                           min_size=min_size, seed=cseed + 1, p_shift=p_shift_all)
         else:
             cats[to_classify] = None
         for j, g in enumerate(tofit):
             cats_all[g] = cats[j]
+        lap("classify")
     # zero test (R/scDD.R:517-526): DZ for the genes the nonzero test did not categorise, NS for the rest
     pvals_z = np.full(ngenes, np.nan)
     if testZeroes:
@@ -397,6 +349,7 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
                 cats_all[g] = "DZ"
             elif categorize:
                 cats_all[g] = "NS"
+    lap("testZeroes")
     # Zhat matrices (R/scDD.R:528-552): 0 = zero count, 1 = default for untested nonzero, else cluster label
     if categorize:
         MAP = hp.labels_to_dense(X, cond, cls_oa, off, genes=tofit, ref=ref)
@@ -404,6 +357,8 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
         MAP2 = hp.labels_to_dense(X, cond, cls_c, off, genes=tofit, which=1, ref=ref)
     else:
         MAP1 = MAP2 = MAP = "Categorize set to FALSE; no clustering provided."
+
+    lap("Zhat")
 
     def _spread(v):
         out = np.full(ngenes, np.nan)
@@ -421,6 +376,8 @@ def scDD(SCdat, prior_param=None, permutations=0, testZeroes=True, adjust_perms=
     SCdat.metadata["Zhat.combined"] = MAP
     SCdat.metadata["Zhat.c1"] = MAP1
     SCdat.metadata["Zhat.c2"] = MAP2
+    lap("assemble")
+    stats["host_phases_s"] = phases
     SCdat.metadata["_scdd_b200"] = {"stats": stats, "tofit": tofit, "fits": fits, "bf": bf, "den": den}
     return SCdat
 

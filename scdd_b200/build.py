@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscdd_b200.so")
 SOURCES = ["scdd_lib.cu"]
-DEPS = ["scdd_lib.cu", "kernels.cuh", "fitset.cuh", "device_math.cuh", "rrng.h", "dense_host.h", "fedp.cuh", "zeroes.cuh", os.path.join("..", "..", "include", "scdd_b200.h")]
+DEPS = ["scdd_lib.cu", "kernels.cuh", "fitset.cuh", "device_math.cuh", "rrng.h", "dense_host.h", "fedp.cuh", "zeroes.cuh", "classify.cuh", os.path.join("..", "..", "include", "scdd_b200.h")]
 
 
 def nvcc_path():

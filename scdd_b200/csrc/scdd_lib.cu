@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "fedp.cuh"
 #include "zeroes.cuh"
+#include "classify.cuh"
 #include "dense_host.h"
 
 using namespace scdd;
@@ -1436,6 +1437,212 @@ int32_t scdd_dense_cell_covariate(const double* X, int64_t ngenes, int64_t ncell
     if (!dense::cell_values_to_csr(v, cell_values, genes, nsel, gene_off, out))
         return fail(SCDD_ERR_BAD_ARG, "gene_off does not match the nonzero cells of the selected genes");
     return SCDD_OK;
+}
+
+// ---- classifyDD, R/classify.dd.R:86-238 ----
+namespace {
+struct GeneClusters {           // what classifyDD derives from one gene's three clusterings
+    int n_oa, n_c1, n_c2;       // luOutlier of oa / c1 / c2
+    int first, count;           // its comparisons in the flat list
+};
+
+// R/classify.dd.R:124-158: labels above the FIRST missing one move down by one (the reference handles one gap)
+inline void compress_labels(std::vector<int>& cls) {
+    int mx = 0, present = 0;
+    bool has[SCDD_GMAX + 2] = {false};
+    for (int l : cls) if (l >= 1 && l <= SCDD_GMAX) { has[l] = true; mx = std::max(mx, l); }
+    for (int l = 1; l <= mx; l++) present += has[l];
+    if (present == mx) return;
+    int missing = 1;
+    while (has[missing]) missing++;
+    for (int& l : cls) if (l > missing) l--;
+}
+
+struct Posterior { double nk[SCDD_GMAX], mk[SCDD_GMAX], sk[SCDD_GMAX], ak[SCDD_GMAX], bk[SCDD_GMAX]; };
+
+// getPosteriorParams, R/classify.dd.R:19-37: normal-gamma posterior of every cluster label 1..GMAX
+inline void posterior_params(const std::vector<double>& y, const std::vector<int>& cls, const scdd_cfg& c, Posterior& P) {
+    double sy[SCDD_GMAX] = {0}, syy[SCDD_GMAX] = {0};
+    for (int k = 0; k < SCDD_GMAX; k++) P.nk[k] = 0;
+    for (size_t i = 0; i < y.size(); i++) {
+        const int l = cls[i];
+        if (l < 1 || l > SCDD_GMAX) continue;
+        P.nk[l - 1] += 1.0; sy[l - 1] += y[i]; syy[l - 1] += y[i] * y[i];
+    }
+    for (int k = 0; k < SCDD_GMAX; k++) {
+        P.sk[k] = c.s0 + P.nk[k];
+        P.mk[k] = (c.s0 * c.m0 + sy[k]) / P.sk[k];
+        P.ak[k] = c.a0 + P.nk[k];
+        P.bk[k] = c.b0 + syy[k] + c.s0 * c.m0 * c.m0 - P.sk[k] * P.mk[k] * P.mk[k];
+    }
+}
+}  // namespace
+
+void scdd_default_classify_opts(scdd_classify_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->ndraws = 10000;
+    o->seed = 1;
+}
+
+int32_t scdd_classify(const double* logy, const int64_t* gene_off, const int32_t* cond01, int32_t ngenes,
+                      const int32_t* cls_oa, const int32_t* cls_c, const int32_t* genes, int32_t nsel,
+                      const double* p_shift, const scdd_cfg* cfg, const scdd_classify_opts* opts,
+                      int32_t* category, scdd_stats* stats) {
+    scdd_cfg dcfg;
+    scdd_default_cfg(&dcfg);
+    if (!cfg) cfg = &dcfg;
+    int rc = check_common(logy, gene_off, cond01, ngenes, cfg);
+    if (rc) return rc;
+    if (nsel < 0 || (nsel > 0 && (!genes || !category || !cls_oa || !cls_c))) return fail(SCDD_ERR_BAD_ARG, "null pointer");
+    scdd_classify_opts o;
+    scdd_default_classify_opts(&o);
+    if (opts) o = *opts;
+    if (o.ndraws < 1) return fail(SCDD_ERR_BAD_ARG, "ndraws must be positive");
+    for (int j = 0; j < nsel; j++)
+        if (genes[j] < 0 || genes[j] >= ngenes) return fail(SCDD_ERR_BAD_ARG, "gene index out of range");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nsel == 0) return SCDD_OK;
+    return guarded([&]() -> int {
+        // ---- host, threaded over the selected genes: label bookkeeping, posteriors, the list of comparisons ----
+        std::vector<GeneClusters> gc((size_t)nsel);
+        std::vector<std::vector<McPair>> per_gene((size_t)nsel);
+        const int ms = cfg->min_size;
+        dense::parallel_ranges(nsel, 64, [&](int64_t lo, int64_t hi) {
+            std::vector<int> oa, c1, c2;
+            std::vector<double> y1, y2;
+            for (int64_t j = lo; j < hi; j++) {
+                const int g = genes[j];
+                const int64_t b = gene_off[g], e = gene_off[g + 1];
+                oa.clear(); c1.clear(); c2.clear(); y1.clear(); y2.clear();
+                for (int64_t i = b; i < e; i++) {
+                    oa.push_back(cls_oa[i]);
+                    if (cond01[i] == 0) { c1.push_back(cls_c[i]); y1.push_back(logy[i]); }
+                    else { c2.push_back(cls_c[i]); y2.push_back(logy[i]); }
+                }
+                compress_labels(oa); compress_labels(c1); compress_labels(c2);
+                auto big = [&](const std::vector<int>& cls, int* labs) {    // findOutliers: labels with >= min.size members
+                    int cnt[SCDD_GMAX + 1] = {0}, n = 0;
+                    for (int l : cls) if (l >= 1 && l <= SCDD_GMAX) cnt[l]++;
+                    for (int l = 1; l <= SCDD_GMAX; l++) if (cnt[l] >= ms && cnt[l] > 0) labs[n++] = l;
+                    return n;
+                };
+                int l_oa[SCDD_GMAX], l1[SCDD_GMAX], l2[SCDD_GMAX];
+                GeneClusters& G = gc[(size_t)j];
+                G.n_oa = big(oa, l_oa); G.n_c1 = big(c1, l1); G.n_c2 = big(c2, l2);
+                Posterior P1, P2;
+                posterior_params(y1, c1, *cfg, P1);
+                posterior_params(y2, c2, *cfg, P2);
+                for (int a = 0; a < G.n_c1; a++)
+                    for (int q = 0; q < G.n_c2; q++) {
+                        const int ka = l1[a] - 1, kb = l2[q] - 1;
+                        McPair m;
+                        m.df1 = std::max(1.0, std::nearbyint(P1.ak[ka]));              // rt(df = round(ak)), :173
+                        m.scale1 = std::sqrt(P1.bk[ka] / (P1.ak[ka] * P1.sk[ka]));
+                        m.m1 = P1.mk[ka];
+                        m.df2 = std::max(1.0, std::nearbyint(P2.ak[kb]));
+                        m.scale2 = std::sqrt(P2.bk[kb] / (P2.ak[kb] * P2.sk[kb]));
+                        m.m2 = P2.mk[kb];
+                        per_gene[(size_t)j].push_back(m);
+                    }
+            }
+        });
+        std::vector<McPair> pairs;
+        for (int j = 0; j < nsel; j++) {
+            gc[(size_t)j].first = (int)pairs.size();
+            gc[(size_t)j].count = (int)per_gene[(size_t)j].size();
+            pairs.insert(pairs.end(), per_gene[(size_t)j].begin(), per_gene[(size_t)j].end());
+        }
+        const int ncomp = (int)pairs.size();
+        std::vector<int32_t> flags((size_t)ncomp, 0);
+        std::vector<double> lohi(o.comp_detail ? (size_t)ncomp * 2 : 0);
+        // ---- device: the Monte-Carlo draws, one warp per comparison ----
+        if (ncomp > 0) {
+            std::vector<int> devs = active_devices();
+            CK(cudaSetDevice(devs[0]));
+            cudaStream_t s;
+            CK(cudaStreamCreate(&s));
+            struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+            struct Events {
+                cudaEvent_t a = nullptr, b = nullptr;
+                ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+            } ev;
+            CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+            DevBuf<McPair> d_pairs;
+            DevBuf<int32_t> d_flags;
+            DevBuf<double> d_lohi;
+            d_pairs.alloc((size_t)ncomp); d_flags.alloc((size_t)ncomp);
+            if (o.comp_detail) d_lohi.alloc((size_t)ncomp * 2);
+            CK(cudaMemcpyAsync(d_pairs.p, pairs.data(), (size_t)ncomp * sizeof(McPair), cudaMemcpyHostToDevice, s));
+            int n_sm = 0;
+            CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devs[0]));
+            const int wpb = 4;
+            const int blocks = std::max(1, std::min((ncomp + wpb - 1) / wpb, n_sm * 16));
+            CK(cudaEventRecord(ev.a, s));
+            classify_mc_kernel<<<blocks, wpb * 32, 0, s>>>(d_pairs.p, ncomp, o.ndraws, (unsigned long long)o.seed, d_flags.p,
+                                                           o.comp_detail ? d_lohi.p : nullptr);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ev.b, s));
+            CK(cudaMemcpyAsync(flags.data(), d_flags.p, (size_t)ncomp * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            if (o.comp_detail) CK(cudaMemcpyAsync(lohi.data(), d_lohi.p, (size_t)ncomp * 16, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (stats) {
+                float ms_k = 0;
+                CK(cudaEventElapsedTime(&ms_k, ev.a, ev.b));
+                stats->total_ms = ms_k;
+                stats->h2d_bytes = (double)ncomp * sizeof(McPair);
+                stats->d2h_bytes = (double)ncomp * (o.comp_detail ? 20 : 4);
+            }
+        }
+        // ---- the decision tree, :189-234 ----
+        for (int j = 0; j < nsel; j++) {
+            const GeneClusters& G = gc[(size_t)j];
+            int tot = 0;
+            for (int t = 0; t < G.count; t++) tot += flags[(size_t)(G.first + t)];
+            int cat = SCDD_CAT_NC;
+            if (G.n_c1 == G.n_c2) {
+                if (G.n_c1 == 1) cat = tot > 0 ? SCDD_CAT_DE : SCDD_CAT_NC;
+                else if (G.n_oa == G.n_c1) cat = tot <= G.n_c1 ? SCDD_CAT_DP : SCDD_CAT_NC;
+                else if (G.n_oa > G.n_c1) {
+                    // multimodal DE: every cross pair but the matching ones differs AND the overall mean shifts (:206-214)
+                    if (tot > G.n_c1 * (G.n_c1 - 1)) cat = (p_shift && p_shift[genes[j]] < 0.01) ? SCDD_CAT_DE : SCDD_CAT_NC;
+                }
+            } else {
+                cat = tot == G.count ? SCDD_CAT_DB : SCDD_CAT_DM;
+            }
+            category[j] = cat;
+        }
+        if (o.comp_off) {
+            for (int j = 0; j < nsel; j++) o.comp_off[j] = gc[(size_t)j].first;
+            o.comp_off[nsel] = ncomp;
+        }
+        if (o.comp_detail) {
+            const int64_t m = std::min<int64_t>(ncomp, o.comp_cap);
+            for (int64_t t = 0; t < m; t++) {
+                double* d = o.comp_detail + t * 9;
+                const McPair& q = pairs[(size_t)t];
+                d[0] = q.df1; d[1] = q.scale1; d[2] = q.m1; d[3] = q.df2; d[4] = q.scale2; d[5] = q.m2;
+                d[6] = (double)flags[(size_t)t]; d[7] = lohi[(size_t)t * 2]; d[8] = lohi[(size_t)t * 2 + 1];
+            }
+        }
+        return SCDD_OK;
+    });
+}
+
+int32_t scdd_selftest_student_t(double df, int32_t n, uint64_t seed, double* out) {
+    if (n < 0 || (n > 0 && !out) || !(df >= 1.0)) return fail(SCDD_ERR_BAD_ARG, "bad arguments");
+    if (device_count_quiet() < 1) return fail(SCDD_ERR_NO_DEVICE, "no CUDA device available: libscdd_b200 has no CPU fallback");
+    if (n == 0) return SCDD_OK;
+    return guarded([&]() -> int {
+        std::vector<int> devs = active_devices();
+        CK(cudaSetDevice(devs[0]));
+        DevBuf<double> d;
+        d.alloc((size_t)n);
+        student_t_kernel<<<(n + 127) / 128, 128>>>(df, n, (unsigned long long)seed, d.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out, d.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        return SCDD_OK;
+    });
 }
 
 void scdd_default_glm_opts(scdd_glm_opts* o) {

@@ -273,6 +273,46 @@ def fedp(logy, cond01, gene_off, cls_oa, cls_c, cdr=None, min_size=3):
     return p_shift, p_fisher, counts, st.as_dict()
 
 
+def classify(logy, cond01, gene_off, genes, cls_oa, cls_c, p_shift=None, cfg=None, seed=1, ndraws=10000, detail=False):
+    """classifyDD (R/classify.dd.R:86-238) for the genes `genes` (0-based) of the block: returns (categories, stats) with
+    categories an object array of "DE" / "DP" / "DM" / "DB" / "NC", or (categories, comp_off, comp_detail, stats) where
+    comp_detail[t] = df1, scale1, m1, df2, scale2, m2, flag, min, max of comparison t (see scdd_classify)."""
+    cfg = cfg or make_cfg()
+    logy = np.ascontiguousarray(logy, dtype=np.float64)
+    cond01 = np.ascontiguousarray(cond01, dtype=np.int32)
+    gene_off = np.ascontiguousarray(gene_off, dtype=np.int64)
+    cls_oa = np.ascontiguousarray(cls_oa, dtype=np.int32)
+    cls_c = np.ascontiguousarray(cls_c, dtype=np.int32)
+    genes = np.ascontiguousarray(genes, dtype=np.int32)
+    if p_shift is not None:
+        p_shift = np.ascontiguousarray(p_shift, dtype=np.float64)
+    ng, nsel = gene_off.size - 1, genes.size
+    o = _lib.ClassifyOpts()
+    _lib.lib().scdd_default_classify_opts(C.byref(o))
+    o.seed, o.ndraws = int(seed), int(ndraws)
+    comp_off = comp = None
+    if detail:
+        comp_off = np.zeros(nsel + 1, dtype=np.int64)
+        comp = np.zeros((max(1, nsel) * 25, 9), dtype=np.float64)
+        o.comp_off, o.comp_detail, o.comp_cap = comp_off.ctypes.data, comp.ctypes.data, comp.shape[0]
+    cat = np.zeros(nsel, dtype=np.int32)
+    st = Stats()
+    _lib.check(_lib.lib().scdd_classify(logy.ctypes.data, gene_off.ctypes.data, cond01.ctypes.data, ng, cls_oa.ctypes.data,
+                                        cls_c.ctypes.data, genes.ctypes.data, nsel, _lib.ptr(p_shift), C.byref(cfg),
+                                        C.byref(o), cat.ctypes.data, C.byref(st)))
+    names = np.array(_lib.CATEGORIES, dtype=object)[cat]
+    if detail:
+        return names, comp_off, comp[:int(comp_off[-1])], st.as_dict()
+    return names, st.as_dict()
+
+
+def student_t_draws(df, n, seed=1):
+    """n variates of the device's Student-t generator (the one behind classify): for distribution tests"""
+    out = np.zeros(int(n), dtype=np.float64)
+    _lib.check(_lib.lib().scdd_selftest_student_t(float(df), int(n), int(seed), out.ctypes.data))
+    return out
+
+
 def gene_seeds(seed, ngenes):
     """L'Ecuyer-CMRG state of every bplapply element for RNGseed = seed (see scdd_rng_gene_seeds)."""
     out = np.zeros((ngenes, 6), dtype=np.uint32)

@@ -197,43 +197,3 @@ def test_two_rank_gene_sharding_gloo(tmp_path):
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "GLOO_OK" in r.stdout
-
-
-def test_classifydd_decision_tree_on_clear_cases():
-    """classifyDD (R/classify.dd.R:86-238) on clusterings whose pattern is unambiguous; no GPU involved (the
-    mean-shift p-values the multimodal-DE rule needs are passed in)"""
-    rng = np.random.default_rng(3)
-    pri = dict(alpha=0.01, mu0=0.0, s0=0.01, a0=0.01, b0=0.01)
-
-    def gene(c1_spec, c2_spec, oa_k):
-        """spec: list of (mean, count); returns y, cond01, class vectors with labels ordered by mean"""
-        ys, cs, l1, l2 = [], [], [], []
-        for k, (m, cnt) in enumerate(c1_spec):
-            ys.append(rng.normal(m, 0.1, cnt)); cs.append(np.zeros(cnt, dtype=np.int32)); l1.append(np.full(cnt, k + 1))
-        for k, (m, cnt) in enumerate(c2_spec):
-            ys.append(rng.normal(m, 0.1, cnt)); cs.append(np.ones(cnt, dtype=np.int32)); l2.append(np.full(cnt, k + 1))
-        y, c = np.concatenate(ys), np.concatenate(cs)
-        cls_c = np.concatenate(l1 + l2).astype(np.int32)
-        # overall clustering: oa_k clusters by thresholding between the distinct means
-        means = sorted(set(m for m, _ in c1_spec + c2_spec))
-        cuts = [(means[i] + means[i + 1]) / 2 for i in range(len(means) - 1)][:oa_k - 1]
-        cls_oa = (1 + sum((y > t).astype(np.int32) for t in cuts)).astype(np.int32) if cuts else np.ones(y.size, dtype=np.int32)
-        return y, c, cls_oa, cls_c
-
-    cases = [("DE", gene([(1.0, 50)], [(3.0, 50)], 2)),
-             ("NC", gene([(2.0, 50)], [(2.0, 50)], 1)),
-             ("DB", gene([(1.0, 30), (5.0, 30)], [(3.0, 60)], 3)),
-             ("DM", gene([(1.0, 30), (5.0, 30)], [(1.0, 60)], 2)),
-             ("DP", gene([(1.0, 18), (5.0, 42)], [(1.0, 42), (5.0, 18)], 2)),
-             ("DE", gene([(1.0, 30), (3.0, 30)], [(5.0, 30), (7.0, 30)], 4))]       # multimodal DE: 2 + 2 clusters, 4 overall
-    ys, cs, oas, ccs = zip(*[g for _, g in cases])
-    off = np.r_[0, np.cumsum([y.size for y in ys])].astype(np.int64)
-    got = api.classifyDD(np.concatenate(ys), np.concatenate(cs), off, np.arange(len(cases)), np.concatenate(oas),
-                         np.concatenate(ccs), pri, rng=np.random.default_rng(1), p_shift=np.full(len(cases), 1e-6))
-    assert got.tolist() == [w for w, _ in cases]
-    # the multimodal-DE rule needs the overall mean shift as well
-    got2 = api.classifyDD(np.concatenate(ys), np.concatenate(cs), off, np.array([5]), np.concatenate(oas),
-                          np.concatenate(ccs), pri, rng=np.random.default_rng(1), p_shift=np.full(len(cases), 0.5))
-    assert got2.tolist() == ["NC"]
-    # a gap in the label set is closed before the posterior parameters are taken (R/classify.dd.R:124-158)
-    assert api._compress_labels(np.array([1, 3, 3, 1])).tolist() == [1, 2, 2, 1]

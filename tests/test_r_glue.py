@@ -209,6 +209,12 @@ def test_glue_on_gpu_matches_ctypes_binding(glue, golden_dir):
     fe = glue.call("C_scdd_fedp", glue.real(vals), glue.real(off), glue.int(c), glue.int(cls_oa), glue.int(cls_c), glue.nil, glue.int([3]))
     ps, pf, cnt, _ = hp.fedp(vals, c, off, cls_oa, cls_c)
     assert np.array_equal(glue.get(fe, "p.shift"), ps, equal_nan=True) and np.array_equal(glue.get(fe, "counts"), cnt.T)
+    # classifyDD: 1-based genes in, category codes out -- the same call through ctypes gives the same labels
+    sel = np.array([2, 5, 11, 20])
+    cd = glue.call("C_scdd_classify", glue.real(vals), glue.real(off), glue.int(c), glue.int(cls_oa), glue.int(cls_c),
+                   glue.int(sel), glue.real(ps), glue.real(PRI), glue.int([3]), glue.int([7]))
+    names = hp.classify(vals, c, off, sel - 1, cls_oa, cls_c, p_shift=ps, cfg=cfg, seed=7)[0]
+    assert [("NC", "DE", "DP", "DM", "DB")[k] for k in glue.value(cd)] == names.tolist()
     # testZeroes: 1-based rows in, NA_real_ (payload 1954) for a gene without zeros
     Xz = np.array(X, dtype=np.float64)
     Xz[2] = np.abs(Xz[2]) + 1.0
