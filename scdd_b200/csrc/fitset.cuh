@@ -13,6 +13,7 @@
 // mclust's quantile initialisation a lookup).  Threads own points i = tid, tid + team size, ...; sufficient
 // statistics are reduced with warp shuffles (plus one shared-memory hop for CTA teams).  All arithmetic is fp64.
 #pragma once
+#include <utility>
 #include <cfloat>
 #include <cstdint>
 
@@ -480,9 +481,20 @@ __device__ __forceinline__ auto load_params(const double* pm) {
 #endif
 }
 
+// one full staging batch: STAGE_K 8-byte cp.async with immediate offsets off one shared and one global base address
+constexpr int STAGE_K = 16;
+template <int NT, int J>
+__device__ __forceinline__ void stage_copy_one(unsigned dst, size_t src) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%2], 8;" ::"r"(dst), "l"(src), "n"(J * NT * 8) : "memory");
+}
+template <int NT, int... J>
+__device__ __forceinline__ void stage_copy_full(unsigned dst, size_t src, std::integer_sequence<int, J...>) {
+    (stage_copy_one<NT, J>(dst, src), ...);
+}
+
 template <int G, int U, int TW, bool SAT>
 __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n, int lane, const double* pm,
-                                           double (&v)[16]) {
+                                           double (&v)[16], double* stage = nullptr, int stage_k = 0) {
     constexpr int NT = Team<TW>::NT;
     const auto prm = load_params<G>(pm);
     double A[G], B[G], C[G];
@@ -500,8 +512,9 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
         const double* px = xs + base + Team<TW>::tid(lane);
         const double* const pend = xs + stop;
         if (U == 1) {
-            if (TW == 1) {
-                // a warp's slab is always shared memory: 32-bit shared-window addresses for the load and the bound test
+            if (TW == 1 || stage == nullptr) {
+                // the slab is shared memory (always for a warp; for a multi-warp team unless it did not fit): 32-bit
+                // shared-window addresses for the load and the bound test
                 unsigned sx = (unsigned)__cvta_generic_to_shared(px);
                 const unsigned send = (unsigned)__cvta_generic_to_shared(pend);
 #pragma unroll 1
@@ -511,19 +524,50 @@ __device__ __forceinline__ void estep_pass(const double* __restrict__ xs, int n,
                     accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
                 }
             } else {
-                // CTA teams: the slab may live in global memory (L2) -- fit-sets beyond 16k points, all of config 5 --
-                // so the loads run three points ahead of the arithmetic instead of opening every iteration with an
-                // L2 round trip
-                double x0 = (px < pend) ? *px : 0.0;
-                double x1 = (px + NT < pend) ? px[NT] : 0.0;
-                double x2 = (px + 2 * NT < pend) ? px[2 * NT] : 0.0;
+                // CTA teams whose slab lives in global memory (L2) -- fit-sets beyond 16k points, all of config 5.
+                // Every thread stages ITS OWN points through shared memory in batches of stage_k with cp.async, two
+                // batches in flight (the tile the sort used is free by now): no registers hold loads in flight, no
+                // barrier is needed (a thread only reads what its own copies wrote), and the arithmetic runs the
+                // same shared-memory loop as above instead of a loop that opens every iteration with an L2 round trip.
+                const int mine = (px < pend) ? (int)((pend - px + NT - 1) / NT) : 0;      // this thread's points in the chunk
+                const int K = stage_k;
+                const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)Team<TW>::tid(lane) * 8u;
+                const unsigned bstride = (unsigned)K * NT * 8u;                           // one buffer
+                const size_t gpx = __cvta_generic_to_global(px);
+                auto issue = [&](int b) {
+                    size_t src = gpx + (size_t)b * K * NT * 8u;
+                    unsigned dst = sbase + (unsigned)(b & 1) * bstride;
+                    const int c = min(K, mine - b * K);
+                    if (K == STAGE_K && c == STAGE_K) {
+                        stage_copy_full<NT>(dst, src, std::make_integer_sequence<int, STAGE_K>());   // immediate offsets
+                    } else {
 #pragma unroll 1
-                while (px < pend) {
-                    double x[1] = {x0};
-                    x0 = x1; x1 = x2;
-                    px += NT;
-                    if (px + 2 * NT < pend) x2 = px[2 * NT];
-                    accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+                        for (int j = 0; j < c; j++) {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                            dst += NT * 8u;
+                            src += NT * 8u;
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                const int nbatch = (mine + K - 1) / K;
+                if (nbatch > 0) issue(0);
+#pragma unroll 1
+                for (int b = 0; b < nbatch; b++) {
+                    if (b + 1 < nbatch) {
+                        issue(b + 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    unsigned sx = sbase + (unsigned)(b & 1) * bstride;
+                    const unsigned send = sx + (unsigned)min(K, mine - b * K) * NT * 8u;
+#pragma unroll 1
+                    for (; sx < send; sx += NT * (unsigned)sizeof(double)) {
+                        double x[1];
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x[0]) : "r"(sx));
+                        accumulate_points<G, 1, SAT>(x, prm, A, B, C, pl, hc, hfar);
+                    }
                 }
             }
         } else {
@@ -599,6 +643,8 @@ struct EmCtx {
     double* pm;
     double* red;
     int n, G, iter, flags;          // flags bit 0: a stop test came within 1e-7 of the tolerance
+    double* stage;                  // staging tile for a slab that lives in global memory (set once by fit_kernel), else null
+    int stage_k, pad;               // points per thread and batch
     double hold, range2, inv_n;
     double sig[GMAX], pro[GMAX];    // mu lives in pm[4 k]
 };
@@ -607,13 +653,13 @@ static_assert(sizeof(EmCtx) % 16 == 0, "keeps the slab 16-byte aligned");
 // same pass with the saturation test (degenerate fits: some variance below range^2 / 2^20); cold code
 template <int TW>
 __device__ __noinline__ double estep_dispatch_sat(int G, const double* xs, int n, int lane, const double* pm,
-                                                  double* red) {
+                                                  double* red, double* stage, int stage_k) {
     double v[16];
     switch (G) {
-        case 2: estep_pass<2, 1, TW, true>(xs, n, lane, pm, v); break;
-        case 3: estep_pass<3, 1, TW, true>(xs, n, lane, pm, v); break;
-        case 4: estep_pass<4, 1, TW, true>(xs, n, lane, pm, v); break;
-        default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, v); break;
+        case 2: estep_pass<2, 1, TW, true>(xs, n, lane, pm, v, stage, stage_k); break;
+        case 3: estep_pass<3, 1, TW, true>(xs, n, lane, pm, v, stage, stage_k); break;
+        case 4: estep_pass<4, 1, TW, true>(xs, n, lane, pm, v, stage, stage_k); break;
+        default: estep_pass<5, 1, TW, true>(xs, n, lane, pm, v, stage, stage_k); break;
     }
     return Team<TW>::reduce(v, lane, red);
 }
@@ -632,18 +678,21 @@ __device__ __noinline__ double estep_ctx(const EmCtx* cx, int lane) {
     // pointers that went through memory have lost their address space: say it again (LDS instead of generic loads)
     __builtin_assume(__isShared(pm));
     if (TW == 1) __builtin_assume(__isShared(xs));
+    double* stage = TW == 1 ? nullptr : cx->stage;
+    const int stage_k = TW == 1 ? 0 : cx->stage_k;
     double v[16];
     switch (G) {
-        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, v); break;
-        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, v); break;
-        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, v); break;
-        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, v); break;
+        case 2: estep_pass<2, Unroll<2>::value, TW, false>(xs, n, lane, pm, v, stage, stage_k); break;
+        case 3: estep_pass<3, Unroll<3>::value, TW, false>(xs, n, lane, pm, v, stage, stage_k); break;
+        case 4: estep_pass<4, Unroll<4>::value, TW, false>(xs, n, lane, pm, v, stage, stage_k); break;
+        default: estep_pass<5, Unroll<5>::value, TW, false>(xs, n, lane, pm, v, stage, stage_k); break;
     }
     return Team<TW>::reduce(v, lane, cx->red);
 }
 template <int TW>
 __device__ __noinline__ double estep_ctx_sat(const EmCtx* cx, int lane) {
-    return estep_dispatch_sat<TW>(cx->G, cx->xs, cx->n, lane, cx->pm, cx->red);
+    return estep_dispatch_sat<TW>(cx->G, cx->xs, cx->n, lane, cx->pm, cx->red, TW == 1 ? nullptr : cx->stage,
+                                  TW == 1 ? 0 : cx->stage_k);
 }
 
 template <int TW>

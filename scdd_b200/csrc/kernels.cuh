@@ -500,7 +500,15 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
     double* xs = (TW > 1 && a.xs_global) ? a.xs_global + ((size_t)blockIdx.x * teams + team) * a.np_max
                                          : reinterpret_cast<double*>(region + fit_region_head(TW));
     const bool lead0 = T::lead() && lane == 0;
-    if (lead0) *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lead0) {
+        *st = WarpStats{0, 0, 0, 0, 0, 0, 0, 0, 0};
+        // slab in global memory: the E-step stages it through the sort's tile, 2 buffers x stage_k points per thread
+        EmCtx* cx = reinterpret_cast<EmCtx*>(pm + 4 * GMAX);
+        const int k = (TW > 1 && a.xs_global) ? a.sort_tile / (2 * T::NT) : 0;
+        cx->stage = k > 0 ? reinterpret_cast<double*>(region + fit_region_head(TW)) : nullptr;
+        cx->stage_k = k > STAGE_K ? STAGE_K : k;
+        cx->pad = 0;
+    }
     T::sync();
     const long long total = (long long)a.ngenes * a.nb * a.sets;
     const double NaN = nan("");

@@ -352,6 +352,8 @@ struct Pipeline {
                 int tile = 1;
                 while ((size_t)tile * 2 * sizeof(double) + head <= smem_cap / teams) tile <<= 1;
                 a.sort_tile = (tile >= 1024 && tile < np) ? tile : 0;
+                // the E-step stages such a slab through the same tile (2 buffers x >= 1 point per thread)
+                if (a.sort_tile < 2 * tw * 32) throw ScddError{SCDD_ERR_TOO_LARGE, "no room for the staging tile of a global-memory slab"};
                 smem = (head + (size_t)a.sort_tile * sizeof(double)) * teams;
                 const size_t need = (size_t)grid * teams * np;
                 if (d_xs_scratch.n < need) d_xs_scratch.alloc(need);
