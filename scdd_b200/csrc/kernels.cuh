@@ -176,7 +176,11 @@ __device__ __forceinline__ double permuted_value(const double* vals, const doubl
     return v;
 }
 
-template <class IdxT, int GS>
+// BATCH: the GS lanes of a group consume GS candidates of the stream per round (see the comment in the loop) instead of
+// the leader alone one by one.  Measured (profiles/permgen_batched_r02.txt): slower when many groups share an SM
+// (config 3: 8-lane groups, ~40 genes per SM hide the leader's dependent chain), so it is used for the 32-lane groups
+// that long genes force (config 5: a 50,000-cell gene fills 100 KB, two groups per SM).
+template <class IdxT, int GS, bool BATCH>
 __global__ void permgen_group_kernel(PermgenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / GS;
@@ -280,67 +284,163 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
             int bits = index_bits(m);
             int need = bits / 16 + 1;
             uint64_t vacc = 0;
-            while (__any_sync(FULLMASK, act && i < n)) {
-                refill(act && i < n && used == PG_BLOCK);
-                if (leader && act && i < n) {
-                    // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
-                    if (bits <= 15) {
-                        // ceil(log2 m) <= 15 (m <= 32768; bits only shrinks while a permutation is drawn, so a gene of up
-                        // to 65535 cells spends three quarters of its picks here): one 16-bit chunk per attempt,
-                        // everything fits 32-bit arithmetic
-                        uint32_t mask = (1u << bits) - 1u;
-                        // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the active range
-                        // receives y[i]: the array ends up holding the permutation reversed.
-                        auto take = [&](uint32_t c16) {
-                            const uint32_t v = c16 & mask;
-                            if (v < m) {
-                                const IdxT pick = arr[v];
-                                --m;
-                                arr[v] = arr[m];
-                                arr[m] = pick;
-                                i++;
-                                if ((m & (m - 1)) == 0) {   // ceil(log2 m) changes only at powers of two
-                                    bits = index_bits(m);
-                                    mask = (1u << bits) - 1u;
+            if constexpr (BATCH) {
+                const unsigned grp = (GS == 32) ? FULLMASK : (((1u << (GS & 31)) - 1u) << lead);   // this group's lanes
+                while (__any_sync(FULLMASK, act && i < n)) {
+                    refill(act && i < n && used == PG_BLOCK);
+                    // ---- the candidates of the current block ----
+                    while (__any_sync(FULLMASK, act && i < n && used < PG_BLOCK)) {
+                        const bool live = act && i < n && used < PG_BLOCK;
+                        // (1) A batch of GS candidates at once, one per lane of the group, whenever every decision of the
+                        // batch is certain without knowing the others: R accepts candidate v iff v < m, and m drops by one
+                        // per accepted pick, so lane l's candidate is surely accepted if v + l < m and surely rejected if
+                        // v >= m.  The batch must not reach a power of two (the bit count of R_unif_index changes there),
+                        // must not finish the permutation (candidates after the last pick are not drawn), and its swaps
+                        // must not touch a location twice -- then "all loads, then all stores" equals the serial order.
+                        const int cpc = bits / 16 + 1;                                  // 16-bit chunks per candidate
+                        const int navail = (PG_BLOCK - used) / cpc;
+                        const uint32_t P = m > 1 ? (1u << (31 - __clz((int)(m - 1)))) : 0u;   // largest power of two below m
+                        const bool can = live && need == cpc && bits <= 31 && navail >= 1 && m > 2u * GS && m - (uint32_t)GS > P;
+                        const int nbat = min(GS, navail);
+                        const bool have = can && sl < nbat;
+                        uint32_t v = 0xffffffffu;
+                        if (have) {
+                            const uint16_t* cp = cand + used + sl * cpc;
+                            v = cp[0];
+                            if (cpc == 2) v = (v << 16) | cp[1];
+                            v &= (bits >= 32) ? 0xffffffffu : ((1u << bits) - 1u);
+                        }
+                        const bool acc = have && v < m;
+                        const bool unsure = acc && !(v + (uint32_t)sl < m);
+                        const unsigned b_acc = __ballot_sync(FULLMASK, acc) & grp;
+                        const int na = __popc(b_acc);
+                        const uint32_t my_m = m - (uint32_t)__popc(b_acc & ((1u << lane) - 1u));   // m when this lane's pick is made
+                        const unsigned same = __match_any_sync(FULLMASK, acc ? v : (0x80000000u | (unsigned)lane));
+                        const bool hazard = unsure || (acc && (__popc(same & grp) > 1 || (v + (uint32_t)na >= m && v + 2u <= my_m)));
+                        const unsigned b_haz = __ballot_sync(FULLMASK, hazard);   // outside the &&: every lane must vote
+                        const bool go = can && (b_haz & grp) == 0;
+                        IdxT pick = 0, last = 0;
+                        if (go && acc) { pick = arr[v]; last = arr[my_m - 1]; }
+                        __syncwarp();
+                        if (go && acc) { arr[v] = last; arr[my_m - 1] = pick; }   // y[i] = x[j]; x[j] = x[--m]: the array ends reversed
+                        __syncwarp();
+                        if (go) { i += (uint32_t)na; m -= (uint32_t)na; used += nbat * cpc; }
+                        // (2) otherwise the leader takes up to 2 GS chunks one by one, exactly as R_unif_index / do_sample do
+                        if (leader && live && !go) {
+                            int budget = 2 * GS;
+                            if (bits <= 15) {
+                                // ceil(log2 m) <= 15: one 16-bit chunk per attempt, everything fits 32-bit arithmetic
+                                uint32_t mask = (1u << bits) - 1u;
+                                while (i < n && used < PG_BLOCK && budget-- > 0) {
+                                    const uint32_t c = (uint32_t)cand[used++] & mask;
+                                    if (c < m) {
+                                        const IdxT pk = arr[c];
+                                        --m;
+                                        arr[c] = arr[m];
+                                        arr[m] = pk;
+                                        i++;
+                                        if ((m & (m - 1)) == 0) {   // ceil(log2 m) changes only at powers of two
+                                            bits = index_bits(m);
+                                            mask = (1u << bits) - 1u;
+                                        }
+                                    }
+                                }
+                                need = bits / 16 + 1;
+                            } else {
+                                const uint64_t one = 1;
+                                uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                while (i < n && used < PG_BLOCK && bits > 15 && budget-- > 0) {
+                                    vacc = 65536ULL * vacc + (uint64_t)cand[used++];
+                                    if (--need == 0) {
+                                        const uint64_t c = vacc & mask;
+                                        if (c < (uint64_t)m) {
+                                            const IdxT pk = arr[c];
+                                            --m;
+                                            arr[c] = arr[m];
+                                            arr[m] = pk;
+                                            i++;
+                                            if ((m & (m - 1)) == 0) {
+                                                bits = index_bits(m);
+                                                mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                            }
+                                        }
+                                        vacc = 0;
+                                        need = bits / 16 + 1;
+                                    }
                                 }
                             }
-                        };
-                        // four candidates per shared-memory load while a whole aligned quad is available: the loop is
-                        // latency-bound (few genes per SM fit shared memory), and the candidate load is half of the
-                        // dependent chain of a step
-                        while (i + 4 <= n && (used & 3) == 0 && used + 4 <= PG_BLOCK) {
-                            const uint2 q = *reinterpret_cast<const uint2*>(cand + used);
-                            used += 4;
-                            take(q.x & 0xffffu); take(q.x >> 16); take(q.y & 0xffffu); take(q.y >> 16);
                         }
-                        while (i < n && used < PG_BLOCK) take((uint32_t)cand[used++]);
-                    } else {
-                        const uint64_t one = 1;
-                        uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
-                        while (i < n && used < PG_BLOCK && bits > 15) {
-                            vacc = 65536ULL * vacc + (uint64_t)cand[used++];
-                            if (--need == 0) {
-                                uint64_t v = vacc & mask;
-                                if (v < (uint64_t)m) {
+                        __syncwarp();
+                        i = __shfl_sync(FULLMASK, i, lead);
+                        m = __shfl_sync(FULLMASK, m, lead);
+                        used = __shfl_sync(FULLMASK, used, lead);
+                        bits = __shfl_sync(FULLMASK, bits, lead);
+                        need = __shfl_sync(FULLMASK, need, lead);
+                    }
+                }
+            } else {
+                while (__any_sync(FULLMASK, act && i < n)) {
+                    refill(act && i < n && used == PG_BLOCK);
+                    if (leader && act && i < n) {
+                        // ---- R_unif_index rejection sampling + the swap of do_sample, serial ----
+                        if (bits <= 15) {
+                            // ceil(log2 m) <= 15 (m <= 32768; bits only shrinks while a permutation is drawn, so a gene of up
+                            // to 65535 cells spends three quarters of its picks here): one 16-bit chunk per attempt,
+                            // everything fits 32-bit arithmetic
+                            uint32_t mask = (1u << bits) - 1u;
+                            // y[i] = x[j]; x[j] = x[--m]  (do_sample).  The slot freed at the end of the active range
+                            // receives y[i]: the array ends up holding the permutation reversed.
+                            auto take = [&](uint32_t c16) {
+                                const uint32_t v = c16 & mask;
+                                if (v < m) {
                                     const IdxT pick = arr[v];
                                     --m;
                                     arr[v] = arr[m];
                                     arr[m] = pick;
                                     i++;
-                                    if ((m & (m - 1)) == 0) {
+                                    if ((m & (m - 1)) == 0) {   // ceil(log2 m) changes only at powers of two
                                         bits = index_bits(m);
-                                        mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                        mask = (1u << bits) - 1u;
                                     }
                                 }
-                                vacc = 0;
-                                need = bits / 16 + 1;
+                            };
+                            // four candidates per shared-memory load while a whole aligned quad is available: the loop is
+                            // latency-bound (few genes per SM fit shared memory), and the candidate load is half of the
+                            // dependent chain of a step
+                            while (i + 4 <= n && (used & 3) == 0 && used + 4 <= PG_BLOCK) {
+                                const uint2 q = *reinterpret_cast<const uint2*>(cand + used);
+                                used += 4;
+                                take(q.x & 0xffffu); take(q.x >> 16); take(q.y & 0xffffu); take(q.y >> 16);
+                            }
+                            while (i < n && used < PG_BLOCK) take((uint32_t)cand[used++]);
+                        } else {
+                            const uint64_t one = 1;
+                            uint64_t mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                            while (i < n && used < PG_BLOCK && bits > 15) {
+                                vacc = 65536ULL * vacc + (uint64_t)cand[used++];
+                                if (--need == 0) {
+                                    uint64_t v = vacc & mask;
+                                    if (v < (uint64_t)m) {
+                                        const IdxT pick = arr[v];
+                                        --m;
+                                        arr[v] = arr[m];
+                                        arr[m] = pick;
+                                        i++;
+                                        if ((m & (m - 1)) == 0) {
+                                            bits = index_bits(m);
+                                            mask = (bits >= 64) ? ~0ULL : ((one << bits) - one);
+                                        }
+                                    }
+                                    vacc = 0;
+                                    need = bits / 16 + 1;
+                                }
                             }
                         }
                     }
+                    i = __shfl_sync(FULLMASK, i, lead);
+                    used = __shfl_sync(FULLMASK, used, lead);
+                    __syncwarp();
                 }
-                i = __shfl_sync(FULLMASK, i, lead);
-                used = __shfl_sync(FULLMASK, used, lead);
-                __syncwarp();
             }
             for (uint32_t k = sl; k < n; k += GS) gout[(size_t)b * n + k] = arr[n - 1 - k];
             __syncwarp();

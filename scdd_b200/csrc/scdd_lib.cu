@@ -436,8 +436,12 @@ struct Pipeline {
     }
 
     // GS lanes per gene for permgen_group_kernel: the smallest group that still leaves several warps per SM
+    // dynamic shared memory a permutation-kernel CTA may ask for (B200: 227 KB per CTA).  224 KB lets TWO 50,000-cell
+    // genes (100.6 KB each with their candidate blocks) share an SM: the kernel is latency-bound, so config 5's
+    // permutation time halves against the 200 KB used before
+    static constexpr size_t PERMGEN_SMEM_CAP = 224 * 1024;
     int pick_group_size() const {
-        const size_t cap = 200 * 1024;
+        const size_t cap = PERMGEN_SMEM_CAP;
         const int ib = (int)idx_bytes();
         auto fits = [&](int gs, size_t min_warps) {
             return cap / (permgen_smem_per_group(max_n, ib, gs) * (32 / gs)) >= min_warps;
@@ -456,7 +460,7 @@ struct Pipeline {
     void launch_permgen_gs(cudaStream_t s, PermgenArgs a) {
         static const MrgDecim dc = decimation_by_pow2(GS == 32 ? 5 : (GS == 8 ? 3 : 2));
         a.dc = dc;
-        const size_t cap = 200 * 1024;
+        const size_t cap = PERMGEN_SMEM_CAP;
         const size_t per_warp = permgen_smem_per_group(max_n, (int)sizeof(IdxT), GS) * (32 / GS);
         const int gpw = 32 / GS;
         size_t wpb_max = 4;
@@ -466,8 +470,17 @@ struct Pipeline {
         const size_t smem = per_warp * wpb;
         const int blocks_needed = (ngenes + gpw * wpb - 1) / (gpw * wpb);
         const int grid = std::min(blocks_needed, n_sm * std::max(1, std::min(16, (int)(cap / smem))));
-        CK(cudaFuncSetAttribute(permgen_group_kernel<IdxT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        permgen_group_kernel<IdxT, GS><<<grid, wpb * 32, smem, s>>>(a);
+        // whole-group consumption of the stream where long genes leave few groups per SM (32-lane groups); the leader's
+        // serial loop elsewhere (kernels.cuh, "BATCH")
+        bool batch = GS == 32;
+        if (const char* e = std::getenv("SCDD_PERMGEN_BATCH")) batch = std::atoi(e) != 0;   // A/B switch
+        if (batch) {
+            CK(cudaFuncSetAttribute(permgen_group_kernel<IdxT, GS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            permgen_group_kernel<IdxT, GS, true><<<grid, wpb * 32, smem, s>>>(a);
+        } else {
+            CK(cudaFuncSetAttribute(permgen_group_kernel<IdxT, GS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            permgen_group_kernel<IdxT, GS, false><<<grid, wpb * 32, smem, s>>>(a);
+        }
     }
     template <class IdxT>
     void launch_permgen(cudaStream_t s, const PermgenArgs& a, int gs) {
@@ -486,7 +499,7 @@ struct Pipeline {
         bool with_jit = false;
         {
             const int ib = (int)idx_bytes();
-            const size_t cap = 200 * 1024;
+            const size_t cap = PERMGEN_SMEM_CAP;
             if (permgen_smem_per_group(max_n, ib, 32) <= cap) {
                 with_jit = true;
                 CK(cudaMemsetAsync(d_jit.p, 0xff, (size_t)ngenes * nb * sets * 6 * sizeof(uint32_t), s));

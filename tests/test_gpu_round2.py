@@ -294,8 +294,9 @@ def test_interrupt_hook_stops_between_chunks(golden_dir):
 
 @pytest.mark.parametrize("ncells", [40, 700, 5000, 40000, 70000])
 def test_permutation_kernel_group_sizes_draw_identical_permutations(ncells, monkeypatch):
-    """4, 8 or 32 lanes per gene: the same R permutations (checked through the Bayes-factor numerators and the final
-    stream states, against the host sampler)"""
+    """4, 8 or 32 lanes per gene, candidates consumed by the leader one by one or by the whole group in batches: the
+    same R permutations (checked through the Bayes-factor numerators and the final stream states, against the host
+    sampler)"""
     rng = np.random.default_rng(ncells)
     ng = 7
     rows = [rng.normal(3, 1, size=max(6, int(ncells * f))) for f in (1.0, 0.9, 0.5, 0.31, 0.77, 0.13, 0.62)]
@@ -309,12 +310,15 @@ def test_permutation_kernel_group_sizes_draw_identical_permutations(ncells, monk
     B = 3
     states = np.array([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), B)[1] for g in range(ng)])
     outs = []
-    for gs in ("4", "8", "32"):
+    # lanes per gene x (leader-serial | whole-group batched) consumption of the candidate stream
+    for gs, batch in (("4", "0"), ("8", "0"), ("32", "0"), ("32", "1"), ("8", "1"), ("4", "1")):
         monkeypatch.setenv("SCDD_PERMGEN_GS", gs)
+        monkeypatch.setenv("SCDD_PERMGEN_BATCH", batch)
         out, st, so = hp.perm_bf(logy, c01, off, B, seed6=seeds, cfg=hp.make_cfg(**PRIORS), return_seeds=True)
-        assert np.array_equal(so, states), gs
+        assert np.array_equal(so, states), (gs, batch)
         outs.append(out)
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    monkeypatch.delenv("SCDD_PERMGEN_BATCH")
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
     if ncells <= 5000:
         pi = np.concatenate([hp.sample_perms(seeds[g], int(off[g + 1] - off[g]), B)[0].ravel() for g in range(ng)])
         host, _ = hp.perm_bf(logy, c01, off, B, perm_idx=pi, cfg=hp.make_cfg(**PRIORS))
