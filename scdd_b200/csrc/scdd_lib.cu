@@ -451,6 +451,9 @@ struct Pipeline {
             if ((v == 4 || v == 8 || v == 32) && fits(v, 1)) return v;
         }
         // measured on B200 (profiles/permgen_groups_r02.txt): 8 lanes per gene is the fastest of the three where it fits
+        // -- unless the shard is so small that 8-lane groups leave the SMs with ~4 warps each (a 2,500-gene shard of
+        // an 8-GPU job: 32 lanes per gene is 17 % faster there, profiles/permgen_fewgenes_r02.txt)
+        if (ngenes <= 24 * n_sm && fits(32, 4)) return 32;
         for (int gs : {8})
             if (fits(gs, 4)) return gs;
         return 32;
@@ -470,9 +473,9 @@ struct Pipeline {
         const size_t smem = per_warp * wpb;
         const int blocks_needed = (ngenes + gpw * wpb - 1) / (gpw * wpb);
         const int grid = std::min(blocks_needed, n_sm * std::max(1, std::min(16, (int)(cap / smem))));
-        // whole-group consumption of the stream where long genes leave few groups per SM (32-lane groups); the leader's
-        // serial loop elsewhere (kernels.cuh, "BATCH")
-        bool batch = GS == 32;
+        // whole-group consumption of the stream where long genes leave few groups per SM; the leader's serial loop
+        // elsewhere (kernels.cuh, "BATCH": slower whenever enough genes share an SM to hide the leader's chain)
+        bool batch = GS == 32 && PERMGEN_SMEM_CAP / per_warp < 8;   // fewer than 8 genes per SM (> ~14,000 cells)
         if (const char* e = std::getenv("SCDD_PERMGEN_BATCH")) batch = std::atoi(e) != 0;   // A/B switch
         if (batch) {
             CK(cudaFuncSetAttribute(permgen_group_kernel<IdxT, GS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
