@@ -483,6 +483,47 @@ __global__ void permgen_group_kernel(PermgenArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-gene sorted copy of the values with the original position of every element (one CTA per gene, bitonic sort of
+// (value, index) pairs in shared memory).  A permuted subset of a gene is a sub-multiset of the SAME values, so its
+// sorted order can be read off this copy with a stable partition instead of sorting the subset again for every
+// permutation (fit_kernel, "presorted").  Genes beyond PRESORT_MAX_CELLS are skipped (they run on CTA teams).
+// ------------------------------------------------------------------------------------------------
+constexpr int PRESORT_MAX_CELLS = 4096;   // a warp-team launch has subsets <= 2048 points, hence genes <= 4096 cells
+__global__ void prep_sort_kernel(const double* __restrict__ vals, const int64_t* __restrict__ off, int ngenes,
+                                 double* __restrict__ srt_vals, uint32_t* __restrict__ srt_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x;
+    if (g >= ngenes) return;
+    const int64_t o = off[g];
+    const int n = (int)(off[g + 1] - o);
+    if (n > PRESORT_MAX_CELLS || n < 1) return;
+    int np = 2;
+    while (np < n) np <<= 1;
+    double* key = reinterpret_cast<double*>(smem_raw);
+    uint32_t* idx = reinterpret_cast<uint32_t*>(key + np);
+    for (int j = threadIdx.x; j < np; j += blockDim.x) { key[j] = j < n ? vals[o + j] : INFINITY; idx[j] = (uint32_t)j; }
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const double a = key[i], b = key[l];
+                    const bool up = (i & k) == 0;
+                    // ties broken by index: a total order, so the result does not depend on the network's schedule
+                    const bool gt = a > b || (a == b && idx[i] > idx[l]);
+                    if (gt == up) {
+                        key[i] = b; key[l] = a;
+                        const uint32_t t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { srt_vals[o + j] = key[j]; srt_idx[o + j] = idx[j]; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mixture fits
 // ------------------------------------------------------------------------------------------------
 enum PermKind { PERM_NONE = 0, PERM_I32_1BASED = 1, PERM_U16 = 2, PERM_U32 = 3 };
@@ -528,6 +569,10 @@ struct FitArgs {
     // recorded by permgen_group_kernel per fit-set (JIT_NONE in word 0 = none); nullable (observed data, host-drawn
     // permutations: a constant vector then has no valid model)
     const uint32_t* jit_state;
+    // Per-gene sorted values and the original position of each (prep_sort_kernel); nullable.  Warp teams on the
+    // unadjusted path build the sorted subset from them by a stable partition instead of a sort ("presorted").
+    const double* srt_vals;
+    const uint32_t* srt_idx;
 };
 
 __device__ __forceinline__ uint32_t perm_lookup(const FitArgs& a, int64_t o, int n, int b, uint32_t i) {
@@ -564,9 +609,10 @@ constexpr int FIT_TAB_BYTES = SCDD_EXP_TABLE_SIZE * 8 + SCDD_LOG_TABLE_SIZE * 16
 
 // per-team shared-memory region: {mu, nh, lc, pad} x GMAX | EmCtx | Row[GMAX] | WarpStats | cross-warp reduction
 // scratch (CTA teams) | xs[np] (absent when the vector lives in global memory)
+constexpr int PRESORT_FLAG_BYTES = PRESORT_MAX_CELLS / 8;   // one membership bit per cell of the gene (warp teams)
 __host__ __device__ constexpr size_t fit_region_head(int tw) {
     return 4 * GMAX * sizeof(double) + sizeof(EmCtx) + GMAX * sizeof(Row) + sizeof(WarpStats) +
-           (tw > 1 ? (size_t)tw * 16 * sizeof(double) : 0);
+           (tw > 1 ? (size_t)tw * 16 * sizeof(double) : (size_t)PRESORT_FLAG_BYTES);
 }
 __host__ __device__ constexpr size_t fit_smem_per_warp(int np) {
     return fit_region_head(1) + (size_t)np * sizeof(double);
@@ -640,24 +686,78 @@ __global__ void __launch_bounds__(FIT_MAX_WARPS * 32, 1) fit_kernel(FitArgs a) {
         else if (w == 1) { n = ng - n1; pofs = n1; }
         else { n = ng; pofs = 0; }                       // oa on c(y1, y2)
 
-        // ---- gather the (permuted) subset into the slab, pad to a power of two, sort ----
+        // ---- the (permuted) subset, sorted, in the slab (padded with +Inf to a power of two) ----
         int np = 2;
         while (np < n) np <<= 1;
-        for (int j = tid; j < np; j += T::NT) {
-            double v = INFINITY;
-            if (j < n) {
-                uint32_t i = a.part[o + pofs + j];
-                uint32_t src = perm_lookup(a, o, ng, b, i);
-                SCDD_CHECK(a.stats, i < (uint32_t)ng && src < (uint32_t)ng && np <= a.np_max);
-                v = permuted_value(a.vals, a.fitted, o, i, src);
+        if (TW == 1 && a.srt_vals != nullptr && a.fitted == nullptr && ng <= PRESORT_MAX_CELLS) {
+            // presorted: the subset is a sub-multiset of the gene's values, whose sorted order is known.  Mark the
+            // ORIGINAL positions that this permutation sends into the subset (one bit per cell), then walk the gene's
+            // sorted copy and keep the marked elements in order: O(n) coalesced work instead of a bitonic sort per
+            // fit-set, and bit-identical to it (equal values are interchangeable).
+            if (w == 2) {
+                for (int j = lane; j < np; j += 32) xs[j] = j < n ? a.srt_vals[o + j] : INFINITY;
+            } else {
+                uint32_t* flag = reinterpret_cast<uint32_t*>(red);
+                for (int k = lane; k < (ng + 31) / 32; k += 32) flag[k] = 0u;
+                __syncwarp();
+                // four independent load chains per lane and step (the loops are bound by L2 latency, not by work)
+                constexpr int UF = 4;
+                for (int j0 = 0; j0 < n; j0 += 32 * UF) {
+                    uint32_t pi[UF], src[UF];
+#pragma unroll
+                    for (int u = 0; u < UF; u++) {
+                        const int j = j0 + 32 * u + lane;
+                        pi[u] = j < n ? a.part[o + pofs + j] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UF; u++) src[u] = perm_lookup(a, o, ng, b, pi[u]);
+#pragma unroll
+                    for (int u = 0; u < UF; u++) {
+                        const int j = j0 + 32 * u + lane;
+                        SCDD_CHECK(a.stats, j >= n || (pi[u] < (uint32_t)ng && src[u] < (uint32_t)ng && np <= a.np_max));
+                        if (j < n) atomicOr(&flag[src[u] >> 5], 1u << (src[u] & 31));
+                    }
+                }
+                __syncwarp();
+                int cnt = 0;
+                for (int k0 = 0; k0 < ng; k0 += 32 * UF) {
+                    uint32_t src[UF];
+                    double v[UF];
+#pragma unroll
+                    for (int u = 0; u < UF; u++) {
+                        const int k = k0 + 32 * u + lane;
+                        src[u] = k < ng ? a.srt_idx[o + k] : 0xffffffffu;
+                        v[u] = k < ng ? a.srt_vals[o + k] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UF; u++) {
+                        const bool f = src[u] != 0xffffffffu && ((flag[src[u] >> 5] >> (src[u] & 31)) & 1u);
+                        const unsigned m = __ballot_sync(FULLMASK, f);
+                        if (f) xs[cnt + __popc(m & ((1u << lane) - 1u))] = v[u];
+                        cnt += __popc(m);
+                    }
+                }
+                SCDD_CHECK(a.stats, cnt == n);
+                for (int j = n + lane; j < np; j += 32) xs[j] = INFINITY;
             }
-            xs[j] = v;
+            __syncwarp();
+        } else {
+            for (int j = tid; j < np; j += T::NT) {
+                double v = INFINITY;
+                if (j < n) {
+                    uint32_t i = a.part[o + pofs + j];
+                    uint32_t src = perm_lookup(a, o, ng, b, i);
+                    SCDD_CHECK(a.stats, i < (uint32_t)ng && src < (uint32_t)ng && np <= a.np_max);
+                    v = permuted_value(a.vals, a.fitted, o, i, src);
+                }
+                xs[j] = v;
+            }
+            T::sync();
+            if (TW > 1 && a.xs_global && a.sort_tile > 0 && np > a.sort_tile)
+                team_sort_tiled<TW>(xs, np, lane, reinterpret_cast<double*>(region + fit_region_head(TW)), a.sort_tile);
+            else
+                team_sort<TW>(xs, np, lane);
         }
-        T::sync();
-        if (TW > 1 && a.xs_global && a.sort_tile > 0 && np > a.sort_tile)
-            team_sort_tiled<TW>(xs, np, lane, reinterpret_cast<double*>(region + fit_region_head(TW)), a.sort_tile);
-        else
-            team_sort<TW>(xs, np, lane);
 
         double jp = NaN;
         int comps = 0;

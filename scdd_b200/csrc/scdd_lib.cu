@@ -202,7 +202,9 @@ struct Pipeline {
     int max_n = 0, max_half = 0;
     int n_sm = 0;
     DevCfg cfg;
-    DevBuf<double> d_logy, d_cdr, d_fitted, d_resid, d_jp, d_bf, d_stats;
+    DevBuf<double> d_logy, d_cdr, d_fitted, d_resid, d_jp, d_bf, d_stats, d_srt_vals;
+    DevBuf<uint32_t> d_srt_idx;
+    bool have_presort = false;
     DevBuf<int64_t> d_off;
     DevBuf<int32_t> d_cond, d_n1;
     DevBuf<uint32_t> d_part, d_seeds;
@@ -287,6 +289,18 @@ struct Pipeline {
         if (ng > 0) prep_partition_kernel<<<blocks, wpb * 32, 0, s>>>(d_cond.p, d_off.p, ng, d_part.p, d_n1.p);
         CK(cudaGetLastError());
         adjusted = cdr != nullptr;
+        // sorted copy of every gene for the warp teams' presorted subsets (unadjusted path; env switch for A/B)
+        have_presort = false;
+        if (ng > 0 && !adjusted && max_n <= PRESORT_MAX_CELLS && !(std::getenv("SCDD_NO_PRESORT") && std::atoi(std::getenv("SCDD_NO_PRESORT")))) {
+            d_srt_vals.alloc(nnz); d_srt_idx.alloc(nnz);
+            int np = 2;
+            while (np < max_n) np <<= 1;
+            const size_t sm = (size_t)np * 12;
+            CK(cudaFuncSetAttribute(prep_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            prep_sort_kernel<<<ng, 256, sm, s>>>(d_logy.p, d_off.p, ng, d_srt_vals.p, d_srt_idx.p);
+            CK(cudaGetLastError());
+            have_presort = true;
+        }
         if (adjusted) {
             d_cdr.alloc(nnz); d_fitted.alloc(nnz); d_resid.alloc(nnz);
             CK(cudaMemcpyAsync(d_cdr.p, cdr + base, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -394,6 +408,8 @@ struct Pipeline {
         a.n1 = d_n1.p;
         a.ngenes = ngenes;
         a.gene_order = have_order ? d_gene_order.p : nullptr;
+        a.srt_vals = have_presort ? d_srt_vals.p : nullptr;
+        a.srt_idx = have_presort ? d_srt_idx.p : nullptr;
         a.gene_cost = nullptr;
         a.iter_budget = 0; a.only_deferred = 0; a.deferred = nullptr;
         return a;
