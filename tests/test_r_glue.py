@@ -233,3 +233,59 @@ def test_glue_on_gpu_matches_ctypes_binding(glue, golden_dir):
     assert glue.L.mock_interrupt_checks() == 2
     glue.L.mock_interrupt_after(-1)
     glue.call("C_scdd_set_devices", glue.int([0]))
+
+
+def _strip_r(src):
+    """R source without comments and string contents (delimiters kept), good enough for delimiter / call checks"""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        ch = src[i]
+        if ch == "#":
+            while i < n and src[i] != "\n":
+                i += 1
+        elif ch in "\"'":
+            q = ch
+            out.append(q)
+            i += 1
+            while i < n and src[i] != q:
+                i += 2 if src[i] == "\\" else 1
+            out.append(q)
+            i += 1
+        else:
+            out.append(ch)
+            i += 1
+    return "".join(out)
+
+
+def test_r_files_are_balanced_and_call_registered_routines_with_the_right_arity():
+    """No R interpreter exists here; this is the static part of what R CMD check would say: delimiters balance and
+    every .Call(C_xxx, ...) names a registered routine and passes as many arguments as its registration declares."""
+    glue_src = re.sub(r"/\*.*?\*/", "", open(GLUE).read(), flags=re.S)
+    table = dict((m.group(1), int(m.group(2))) for m in re.finditer(r'\{"(C_scdd_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', glue_src))
+    calls_seen = set()
+    for name in ("scDD_gpu.R", "scDD_b200.R"):
+        src = _strip_r(open(os.path.join(ROOT, "r", "R", name)).read())
+        stack = []
+        pairs = {")": "(", "]": "[", "}": "{"}
+        for ch in src:
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in ")]}":
+                assert stack and stack.pop() == pairs[ch], f"unbalanced {ch} in {name}"
+        assert not stack, f"unclosed {stack[-1]} in {name}"
+        for m in re.finditer(r"\.Call\(\s*(C_scdd_\w+)", src):
+            routine = m.group(1)
+            assert routine in table, f"{name}: {routine} is not registered in scdd_glue.c"
+            depth, nargs, i = 1, 0, m.end()
+            while depth > 0:
+                ch = src[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    nargs += 1
+                i += 1
+            assert nargs == table[routine], f"{name}: .Call({routine}) passes {nargs} arguments, registered with {table[routine]}"
+            calls_seen.add(routine)
+    assert calls_seen == set(table), f"registered but never called from R: {set(table) - calls_seen}"

@@ -97,3 +97,26 @@ def test_oracle_test_zeroes_rules():
     straight = np.where(cond == cond[0], "a", "b")
     pa, pb = zo.test_zeroes(X[:40], straight), zo.test_zeroes(X[:40], flipped)
     assert not np.allclose(pa[ok], pb[ok], rtol=1e-12) and np.allclose(pa[ok], pb[ok], rtol=0.2, atol=0.02)
+
+
+def test_irls_core_against_an_independent_logistic_regression():
+    """With an (almost) flat normal prior -- huge scale, df -> infinity switches the EM update off -- bayesglm's loop
+    is plain IRLS: coefficients must equal scikit-learn's unpenalised maximum-likelihood fit and the standard errors
+    the inverse Fisher information."""
+    from sklearn.linear_model import LogisticRegression
+    X, cond = _fixture("scDatEx")
+    M = _design(X, cond)
+    done = 0
+    for g in range(200):
+        y = (X[g] > 0).astype(np.float64)
+        lvl = M[:, 2] == 1
+        if min(y[lvl].sum(), (1 - y[lvl]).sum(), y[~lvl].sum(), (1 - y[~lvl]).sum()) < 6:
+            continue                                     # (quasi-)separation: the maximum-likelihood fit runs away
+        r = zo.bayesglm_logit(y, M, scale=np.full(3, 1e8), df=1e30, epsilon=1e-14, maxit=200)
+        ref = LogisticRegression(C=np.inf, fit_intercept=False, tol=1e-12, max_iter=5000).fit(M, y)
+        np.testing.assert_allclose(r["coef"], ref.coef_[0], rtol=2e-4, atol=2e-4)
+        mu = 1.0 / (1.0 + np.exp(-(M @ r["coef"])))
+        cov = np.linalg.inv(M.T @ (M * (mu * (1 - mu))[:, None]))
+        np.testing.assert_allclose(r["se"], np.sqrt(np.diag(cov)), rtol=1e-6)
+        done += 1
+    assert done >= 5
