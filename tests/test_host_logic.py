@@ -197,3 +197,19 @@ def test_two_rank_gene_sharding_gloo(tmp_path):
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_fisher_combination_and_factor_levels():
+    """R/scDD.R:570-578 (Fisher's method with R's NA rules) and the level order of factor(cond) (R/classify.dd.R:268)"""
+    from scipy import stats
+    for a, b in [(0.3, 0.04), (1e-5, 0.9), (1.0, 1.0), (1e-300, 1e-300), (0.5, 0.5)]:
+        want = stats.chi2.sf(-2 * (np.log(a) + np.log(b)), 4)
+        np.testing.assert_allclose(api.fishersCombinedPval((a, b)), want, rtol=1e-12, atol=1e-320)
+    assert api.fishersCombinedPval((0.0, 0.5)) == 0.0
+    assert api.fishersCombinedPval((np.nan, 0.2)) == 0.2 and api.fishersCombinedPval((0.7, np.nan)) == 0.7
+    assert np.isnan(api.fishersCombinedPval((np.nan, np.nan)))
+    from scdd_b200 import hotpath as hp
+    assert hp.factor_level2(np.array([2, 1, 2, 1])).tolist() == [1, 0, 1, 0]            # sorted levels, not first-seen
+    assert hp.factor_level2(np.array(["trt", "ctl", "ctl"])).tolist() == [1, 0, 0]
+    with pytest.raises(ValueError):
+        hp.factor_level2(np.array([1, 1, 1]))
